@@ -1,0 +1,212 @@
+// cmux_core.cuh — one CMux step  acc += GGSW (x) ct1  for G ciphertexts resident in one CTA.
+//
+// This is the inner loop of every FP64 stage of the reference's per-byte chain:
+//   * blind rotation inside the PBS of circuit_bootstrap_boolean (many_wopbs.rs:253; 669 steps
+//     with the bootstrap key, beta = 2^8, l = 5) and of the general extract_bits loop (:194),
+//   * the blind-rotation half of vertical_packing (many_wopbs.rs:277; 8-9 steps with the
+//     circuit-bootstrapped GGSWs, beta = 2^15, l = 1),
+//   * the CMux tree of vertical_packing when a LUT spans several polynomials.
+// Arithmetic follows SURVEY.md §9.3-9.6 (signed decomposition, forward FFT of the digits,
+// multiply-accumulate against the Fourier GGSW, inverse FFT, round, add).
+//
+// CTA organisation (256 threads = 16 groups of 16 lanes):
+//   FFT phases:  group g handles polynomial r = g % (K+1) of ciphertext ct = g / (K+1)
+//                (G*(K+1) <= 16 groups busy).  Lane n2 owns coefficients 16 n1 + n2 (+256).
+//   MAC phase:   thread p owns Fourier point p of all G ciphertexts and all K+1 output
+//                polynomials; the GGSW value for (level, row, p, *) is loaded once and used G times.
+// The phases below are separate __host__ __device__ functions so that emu.cu can run them on the CPU
+// thread by thread; the kernels call them with barriers in between.
+#pragma once
+#include "fft_core.cuh"
+
+#define CMUX_THREADS 256
+#define CMUX_GROUPS 16
+#define POLY_N 512
+#define POLY_M 256
+
+enum { DIFF_ROTATE = 0, DIFF_EXTERNAL = 1 };
+
+template <int K, int G>
+struct CmuxSmem {
+    uint64_t acc[G][K + 1][POLY_N];      // the G accumulators (GLWE, standard domain)
+    cd xb[CMUX_GROUPS][XB_ELEMS];        // exchange / hand-over buffers, one per group
+    cd twf[256];                         // forward mid twiddles [k1][n2]
+    cd twi[256];                         // inverse mid twiddles [n2][k1]
+    int rot[G];                          // per-ciphertext rotation amount of the current step, in [0, 2N)
+};
+
+template <int K, int G>
+struct CmuxRegs {
+    cd v[16];              // FFT working set
+    uint32_t st_re[16];    // decomposition state of coefficient 16 n1 + lane
+    uint32_t st_im[16];    // decomposition state of coefficient 16 n1 + lane + 256
+    cd facc[G][K + 1];     // Fourier accumulators of point p = tid
+};
+
+// theta^(e) = exp(2 pi i e / 1024); used once per CTA to fill the twiddle tables
+HD cd theta_pow(int e, const double *cos1024 /* [1024] */, const double *sin1024) {
+    e &= 1023;
+    return cmk(cos1024[e], sin1024[e]);
+}
+
+// coefficient j of (acc * X^rot): rot in [0, 2N)
+HD uint64_t rotated_coef(const uint64_t *poly, int j, int rot) {
+    int s = (j - rot) & (2 * POLY_N - 1);
+    uint64_t x = poly[s & (POLY_N - 1)];
+    return (s & POLY_N) ? (uint64_t)0 - x : x;
+}
+
+// First decomposition step from the full 64-bit value: returns the digit of level LEVELS and leaves
+// the (<= 32-bit) state for the remaining levels.
+template <int BASE_LOG, int LEVELS>
+HD int decomp_first(uint64_t x, uint32_t &state) {
+    constexpr int R = 64 - BASE_LOG * LEVELS;
+    uint64_t s = ((x >> R) + ((x >> (R - 1)) & 1)) & (~0ull >> R);
+    uint32_t res = (uint32_t)s & ((1u << BASE_LOG) - 1);
+    uint32_t st = (uint32_t)(s >> BASE_LOG);
+    uint32_t carry = (((res - 1u) | st) & res) >> (BASE_LOG - 1);
+    state = st + carry;
+    return (int)res - (int)(carry << BASE_LOG);
+}
+template <int BASE_LOG>
+HD int decomp_next(uint32_t &state) {
+    uint32_t res = state & ((1u << BASE_LOG) - 1);
+    uint32_t st = state >> BASE_LOG;
+    uint32_t carry = (((res - 1u) | st) & res) >> (BASE_LOG - 1);
+    state = st + carry;
+    return (int)res - (int)(carry << BASE_LOG);
+}
+
+// ---- phase A: build ct1 = (acc * X^rot - acc) [DIFF_ROTATE] or (ext - acc) [DIFF_EXTERNAL] for the
+// 32 coefficients this lane owns, start the decomposition, emit the digits of the first level into v.
+template <int K, int G, int BASE_LOG, int LEVELS, int MODE>
+HD void phase_load_decompose(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg, const uint64_t *const *ext /* [G] GLWE pointers */) {
+    const int gid = tid >> 4, lane = tid & 15;
+#pragma unroll
+    for (int ct = 0; ct < G; ct++)
+#pragma unroll
+        for (int c = 0; c <= K; c++) rg.facc[ct][c] = cmk(0.0, 0.0);
+    if (gid >= G * (K + 1)) return;
+    const int ct = gid / (K + 1), r = gid % (K + 1);
+    const uint64_t *poly = sm.acc[ct][r];
+    const int rot = sm.rot[ct];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) {
+        const int j = 16 * n1 + lane;
+        uint64_t a0, a1;
+        if (MODE == DIFF_ROTATE) {
+            a0 = rotated_coef(poly, j, rot) - poly[j];
+            a1 = rotated_coef(poly, j + POLY_M, rot) - poly[j + POLY_M];
+        } else {
+            const uint64_t *e = ext[ct] + (size_t)r * POLY_N;
+            a0 = e[j] - poly[j];
+            a1 = e[j + POLY_M] - poly[j + POLY_M];
+        }
+        int d0 = decomp_first<BASE_LOG, LEVELS>(a0, rg.st_re[n1]);
+        int d1 = decomp_first<BASE_LOG, LEVELS>(a1, rg.st_im[n1]);
+        rg.v[n1] = cmk((double)d0, (double)d1);
+    }
+}
+// digits of the next level (level index decreasing)
+template <int K, int G, int BASE_LOG>
+HD void phase_next_digits(int tid, CmuxRegs<K, G> &rg) {
+    if ((tid >> 4) >= G * (K + 1)) return;
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) {
+        int d0 = decomp_next<BASE_LOG>(rg.st_re[n1]);
+        int d1 = decomp_next<BASE_LOG>(rg.st_im[n1]);
+        rg.v[n1] = cmk((double)d0, (double)d1);
+    }
+}
+// ---- forward FFT of the digit polynomial held in v -------------------------------------------
+template <int K, int G>
+HD void phase_fwd1(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) {
+    const int gid = tid >> 4, lane = tid & 15;
+    if (gid >= G * (K + 1)) return;
+    fft256_fwd_pass1(rg.v, lane, sm.twf, sm.xb[gid]);
+}
+template <int K, int G>
+HD void phase_fwd2(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) {
+    const int gid = tid >> 4, lane = tid & 15;
+    if (gid >= G * (K + 1)) return;
+    fft256_fwd_pass2(rg.v, lane, sm.xb[gid]);
+}
+template <int K, int G>
+HD void phase_fwd3(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) {
+    const int gid = tid >> 4, lane = tid & 15;
+    if (gid >= G * (K + 1)) return;
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++) sm.xb[gid][lane + 16 * k2] = rg.v[rev4(k2)];
+}
+// ---- multiply-accumulate of one level against the Fourier GGSW -------------------------------
+// ggsw_level points at [row r][point p][col c] complex of this level.
+template <int K, int G>
+HD void phase_mac(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg, const cd *__restrict__ ggsw_level) {
+    const int p = tid;
+#pragma unroll
+    for (int r = 0; r <= K; r++) {
+        cd w[K + 1];
+        const cd *g = ggsw_level + ((size_t)r * POLY_M + p) * (K + 1);
+#pragma unroll
+        for (int c = 0; c <= K; c++) {
+#ifdef __CUDA_ARCH__
+            w[c] = __ldg(g + c);
+#else
+            w[c] = g[c];
+#endif
+        }
+#pragma unroll
+        for (int ct = 0; ct < G; ct++) {
+            const cd x = sm.xb[ct * (K + 1) + r][p];
+#pragma unroll
+            for (int c = 0; c <= K; c++) cmac(rg.facc[ct][c], x, w[c]);
+        }
+    }
+}
+// ---- inverse transform of the K+1 accumulators of every ciphertext and update of acc ----------
+template <int K, int G>
+HD void phase_inv0(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) {
+    const int p = tid;
+#pragma unroll
+    for (int ct = 0; ct < G; ct++)
+#pragma unroll
+        for (int c = 0; c <= K; c++) sm.xb[ct * (K + 1) + c][p] = rg.facc[ct][c];
+}
+template <int K, int G>
+HD void phase_inv1(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) {
+    const int gid = tid >> 4, lane = tid & 15;
+    if (gid >= G * (K + 1)) return;
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++) rg.v[k2] = sm.xb[gid][lane + 16 * k2];
+    fft256_inv_pass1_compute(rg.v);
+}
+template <int K, int G>
+HD void phase_inv2(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) {
+    const int gid = tid >> 4, lane = tid & 15;
+    if (gid >= G * (K + 1)) return;
+    fft256_inv_pass1_store(rg.v, lane, sm.twi, sm.xb[gid]);
+}
+template <int K, int G>
+HD void phase_inv3(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) {
+    const int gid = tid >> 4, lane = tid & 15;
+    if (gid >= G * (K + 1)) return;
+    const int ct = gid / (K + 1), c = gid % (K + 1);
+    fft256_inv_pass2(rg.v, lane, sm.xb[gid]);
+    uint64_t *poly = sm.acc[ct][c];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) {
+        const int j = 16 * n1 + lane;
+        poly[j] += f64_to_torus(rg.v[n1].x);
+        poly[j + POLY_M] += f64_to_torus(rg.v[n1].y);
+    }
+}
+
+// ---- forward transform of a torus polynomial (key conversion) -----------------
+// lane loads 32 coefficients as signed 64-bit -> f64 (53-bit rounding)
+HD void load_torus_poly(cd (&v)[16], int lane, const uint64_t *poly) {
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) {
+        const int j = 16 * n1 + lane;
+        v[n1] = cmk((double)(int64_t)poly[j], (double)(int64_t)poly[j + POLY_M]);
+    }
+}

@@ -1,0 +1,371 @@
+// engine.cu — context, key preparation and the device-level stages of one WoPBS pass
+// (keyswitch -> PBS -> PFKS -> Fourier GGSW -> vertical packing), i.e. the GPU restatement of
+// many_wopbs_without_padding (many_wopbs.rs:31-116) batched over many encrypted bytes.
+#include <cstdio>
+#include <cstring>
+#include "engine.h"
+#include "twiddle_host.h"
+
+static thread_local std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------------
+int ws_reserve(tfa_ctx *ctx, size_t bytes) {
+    bytes += 1 << 20;
+    if (bytes > ctx->ws_cap) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->ws) CU(cudaFree(ctx->ws));
+        ctx->ws = nullptr; ctx->ws_cap = 0;
+        size_t cap = bytes + bytes / 8;
+        CU(cudaMalloc(&ctx->ws, cap));
+        ctx->ws_cap = cap;
+    }
+    ctx->ws_off = 0;
+    return TFA_OK;
+}
+void *ws_alloc(tfa_ctx *ctx, size_t bytes) {
+    size_t off = (ctx->ws_off + 255) & ~(size_t)255;
+    if (off + bytes > ctx->ws_cap) { ctx->err = "internal: workspace exhausted"; return nullptr; }
+    ctx->ws_off = off + bytes;
+    return ctx->ws + off;
+}
+#define WS(ptr, T, count)                                         \
+    T *ptr = ws_get<T>(ctx, (count));                             \
+    if (!ptr) return TFA_ERR_STATE
+
+int require_keys(tfa_ctx *ctx) {
+    if (!ctx->keys_ready) return ctx->fail(TFA_ERR_STATE, "keys not loaded (tfa_ctx_load_keys / tfa_client_keygen)");
+    return TFA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+static int ilog2u(uint64_t v) { int r = 0; while (v > 1) { v >>= 1; r++; } return r; }
+
+extern "C" void tfa_param_opt(tfa_params *o) {
+    // client.rs:31-57
+    *o = tfa_params{669, 4, 512, 8, 5, 2, 6, 12, 3, 15, 1, 2, 1, 0, 3.0517578125e-05, 3.162026630747649e-16, 3.162026630747649e-16};
+}
+
+extern "C" int tfa_ctx_create(const tfa_params *p, int device, void *stream, tfa_ctx **out) {
+    *out = nullptr;
+    if (!p) { g_create_error = "null params"; return TFA_ERR_PARAM; }
+    if (p->poly_size != 512) { g_create_error = "only polynomial_size 512 is implemented (client.rs:35)"; return TFA_ERR_PARAM; }
+    if (p->glwe_dim != 4 && p->glwe_dim != 1) { g_create_error = "glwe_dimension must be 4 (PARAM_OPT) or 1 (test set)"; return TFA_ERR_PARAM; }
+    if (p->pbs_base_log != 8 || p->pbs_level != 5 || p->cbs_base_log != 15 || p->cbs_level != 1) {
+        g_create_error = "PBS (2^8, 5) and CBS (2^15, 1) decompositions are the compiled kernel variants (client.rs:42-43,51-52)";
+        return TFA_ERR_PARAM;
+    }
+    if (p->ks_base_log * p->ks_level > 63 || p->pfks_base_log * p->pfks_level > 63 || p->ks_base_log > 15 || p->pfks_base_log > 15) {
+        g_create_error = "keyswitch decomposition out of range"; return TFA_ERR_PARAM;
+    }
+    if (p->lwe_dim < 1 || p->lwe_dim > 2048) { g_create_error = "lwe_dimension out of range"; return TFA_ERR_PARAM; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e);
+        return TFA_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "bad device index"; return TFA_ERR_PARAM; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return TFA_ERR_CUDA; }
+    tfa_ctx *ctx = new tfa_ctx();
+    ctx->p = *p;
+    ctx->n = p->lwe_dim; ctx->k = p->glwe_dim; ctx->N = p->poly_size;
+    ctx->big = ctx->k * ctx->N; ctx->lw = ctx->big + 1; ctx->gsz = (ctx->k + 1) * ctx->N;
+    ctx->device = device;
+    ctx->launches = 0;
+    ctx->own_stream = (stream == nullptr);
+    ctx->stream = (cudaStream_t)stream;
+    ctx->bsk_f = nullptr; ctx->ksk = nullptr; ctx->pfpksk = nullptr; ctx->ksk_colsum = nullptr; ctx->pfpksk_colsum = nullptr;
+    ctx->tw = nullptr; ctx->keys_allocated = ctx->keys_ready = false;
+    ctx->d_lwe_sk = ctx->d_glwe_sk = nullptr;
+    for (auto &l : ctx->lut_cache) l = nullptr;
+    ctx->ws = nullptr; ctx->ws_cap = ctx->ws_off = 0;
+    ctx->ks_cols_pad = (ctx->n + 2) & ~1;
+    if (ctx->own_stream) {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return TFA_ERR_CUDA; }
+    }
+    cd tw[512];
+    make_twiddle_tables(tw);
+    e = cudaMalloc(&ctx->tw, sizeof(tw));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->tw, tw, sizeof(tw), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return TFA_ERR_CUDA; }
+    *out = ctx;
+    return TFA_OK;
+}
+extern "C" void tfa_ctx_destroy(tfa_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->bsk_f); cudaFree(ctx->ksk); cudaFree(ctx->pfpksk); cudaFree(ctx->ksk_colsum); cudaFree(ctx->pfpksk_colsum);
+    cudaFree(ctx->tw); cudaFree(ctx->d_lwe_sk); cudaFree(ctx->d_glwe_sk); cudaFree(ctx->ws);
+    for (auto l : ctx->lut_cache) cudaFree(l);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" const char *tfa_last_error(const tfa_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+extern "C" int tfa_ctx_synchronize(tfa_ctx *ctx) { CU(cudaStreamSynchronize(ctx->stream)); return TFA_OK; }
+extern "C" uint64_t tfa_ctx_launch_count(const tfa_ctx *ctx) { return ctx->launches; }
+
+// ------------------------------------------------------------------------------------------------
+// key preparation
+// ------------------------------------------------------------------------------------------------
+extern "C" int tfa_ctx_alloc_keys(tfa_ctx *ctx) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->keys_allocated) return TFA_OK;
+    CU(cudaMalloc(&ctx->bsk_f, ctx->bsk_f_bytes()));
+    CU(cudaMalloc(&ctx->ksk, ctx->ksk_bytes()));
+    CU(cudaMalloc(&ctx->pfpksk, ctx->pfpksk_bytes()));
+    CU(cudaMalloc(&ctx->ksk_colsum, (size_t)ctx->ks_cols_pad * 8));
+    CU(cudaMalloc(&ctx->pfpksk_colsum, (size_t)(ctx->k + 1) * ctx->gsz * 8));
+    ctx->keys_allocated = true;
+    return TFA_OK;
+}
+extern "C" int tfa_ctx_key_buffers(tfa_ctx *ctx, void **ptrs, size_t *bytes, int *count) {
+    if (!ctx->keys_allocated) return ctx->fail(TFA_ERR_STATE, "key buffers not allocated");
+    ptrs[0] = ctx->bsk_f; bytes[0] = ctx->bsk_f_bytes();
+    ptrs[1] = ctx->ksk; bytes[1] = ctx->ksk_bytes();
+    ptrs[2] = ctx->pfpksk; bytes[2] = ctx->pfpksk_bytes();
+    ptrs[3] = ctx->ksk_colsum; bytes[3] = (size_t)ctx->ks_cols_pad * 8;
+    ptrs[4] = ctx->pfpksk_colsum; bytes[4] = (size_t)(ctx->k + 1) * ctx->gsz * 8;
+    *count = 5;
+    return TFA_OK;
+}
+extern "C" int tfa_ctx_keys_ready(tfa_ctx *ctx) {
+    if (!ctx->keys_allocated) return ctx->fail(TFA_ERR_STATE, "key buffers not allocated");
+    ctx->keys_ready = true;
+    return TFA_OK;
+}
+
+// finishes key preparation from standard-domain device buffers: bsk_std [n*l*(k+1)*(k+1) polys],
+// ksk already in padded layout in ctx->ksk, pfpksk already in ctx->pfpksk
+int prepare_keys_from_device(tfa_ctx *ctx, const u64 *bsk_std_dev) {
+    const long npoly = (long)ctx->n * ctx->p.pbs_level * (ctx->k + 1) * (ctx->k + 1);
+    RC(dev_fourier(ctx, bsk_std_dev, npoly, ctx->bsk_f));
+    CU(launch_key_colsum(ctx->ksk, ctx->big * ctx->p.ks_level, ctx->ks_cols_pad, ctx->ks_cols_pad, 1, 0, ctx->ksk_colsum, ctx->stream));
+    const int prow = (ctx->big + 1) * ctx->p.pfks_level;
+    CU(launch_key_colsum(ctx->pfpksk, prow, ctx->gsz, ctx->gsz, ctx->k + 1, (size_t)prow * ctx->gsz, ctx->pfpksk_colsum, ctx->stream));
+    ctx->launches += 2;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->keys_ready = true;
+    return TFA_OK;
+}
+
+extern "C" int tfa_ctx_load_keys(tfa_ctx *ctx, const uint64_t *bsk, const uint64_t *ksk, const uint64_t *pfpksk) {
+    if (!bsk || !ksk || !pfpksk) return ctx->fail(TFA_ERR_PARAM, "null key pointer");
+    RC(tfa_ctx_alloc_keys(ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const size_t bsk_bytes = (size_t)ctx->n * ctx->p.pbs_level * (ctx->k + 1) * ctx->gsz * 8;
+    u64 *tmp = nullptr;
+    CU(cudaMalloc(&tmp, bsk_bytes));
+    CU(cudaMemcpyAsync(tmp, bsk, bsk_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->ksk, 0, ctx->ksk_bytes(), ctx->stream));
+    CU(cudaMemcpy2DAsync(ctx->ksk, (size_t)ctx->ks_cols_pad * 8, ksk, (size_t)(ctx->n + 1) * 8, (size_t)(ctx->n + 1) * 8,
+                         (size_t)ctx->big * ctx->p.ks_level, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->pfpksk, pfpksk, ctx->pfpksk_bytes(), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = prepare_keys_from_device(ctx, tmp);
+    cudaFree(tmp);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stages
+// ------------------------------------------------------------------------------------------------
+static int pick_G(int K, int count) {
+    if (K == 4) return count > 296 ? 3 : (count > 148 ? 2 : 1);
+    return count >= 16 ? 8 : (count >= 4 ? 4 : 1);
+}
+
+int dev_fourier(tfa_ctx *ctx, const u64 *polys, long npoly, double2 *out) {
+    ConvertArgs a{polys, out, ctx->tw, npoly, ctx->k};
+    CU(launch_fourier_convert(a, ctx->stream));
+    ctx->launches++;
+    return TFA_OK;
+}
+
+static int rows_per_split(int rows, int base_ctas) {
+    // aim for >= ~2 waves of CTAs; splits in whole chunks of 512 rows
+    int want = (2 * 148 + base_ctas - 1) / base_ctas;
+    if (want < 1) want = 1;
+    int chunks = (rows + 511) / 512;
+    if (want > chunks) want = chunks;
+    int per = (chunks + want - 1) / want;
+    return per * 512;
+}
+
+// out = (0,..,0,b) - sum_i sum_l d_{i,l} KSK[i][l]
+int dev_keyswitch(tfa_ctx *ctx, const u64 *in, int count, u64 *out) {
+    const int rows = ctx->big * ctx->p.ks_level, np = ctx->n + 1;
+    WS(digits, uint16_t, (size_t)count * rows);
+    CU(launch_decompose(in, ctx->lw, ctx->big, count, ctx->p.ks_base_log, ctx->p.ks_level, digits, ctx->stream));
+    CU(launch_gemv_init(out, np, np, count, ctx->ksk_colsum, 1ull << (ctx->p.ks_base_log - 1), in, ctx->lw, ctx->big, ctx->n, ctx->stream));
+    GemvArgs g{};
+    g.digits = digits; g.key = ctx->ksk; g.out = out; g.key_stride = 0; g.key_row_stride = ctx->ks_cols_pad;
+    g.out_stride = np; g.rows = rows; g.ncols = np; g.nkeys = 1; g.count = count;
+    g.rows_per_split = rows_per_split(rows, ((np + 511) / 512) * ((count + 7) / 8));
+    CU(launch_gemv(g, ctx->stream));
+    ctx->launches += 3;
+    return TFA_OK;
+}
+
+// for every key r: glwe_r = - sum_j sum_l d_{j,l} PFPKSK_r[j][l]; out[b][r][gsz] with stride
+int dev_pfks(tfa_ctx *ctx, const u64 *in, int count, u64 *out, int out_stride) {
+    const int rows = (ctx->big + 1) * ctx->p.pfks_level, kp1 = ctx->k + 1;
+    WS(digits, uint16_t, (size_t)count * rows);
+    CU(launch_decompose(in, ctx->lw, ctx->big + 1, count, ctx->p.pfks_base_log, ctx->p.pfks_level, digits, ctx->stream));
+    CU(launch_gemv_init(out, out_stride, kp1 * ctx->gsz, count, ctx->pfpksk_colsum, 1ull << (ctx->p.pfks_base_log - 1), nullptr, 0, 0, 0, ctx->stream));
+    GemvArgs g{};
+    g.digits = digits; g.key = ctx->pfpksk; g.out = out; g.key_stride = (size_t)rows * ctx->gsz; g.key_row_stride = ctx->gsz;
+    g.out_stride = out_stride; g.rows = rows; g.ncols = ctx->gsz; g.nkeys = kp1; g.count = count;
+    g.rows_per_split = rows_per_split(rows, ((ctx->gsz + 511) / 512) * ((count + 7) / 8) * kp1);
+    CU(launch_gemv(g, ctx->stream));
+    ctx->launches += 3;
+    return TFA_OK;
+}
+
+// SURVEY §9.4(3)
+int dev_pbs(tfa_ctx *ctx, const u64 *in, int count, const u64 *lut, u64 in_scale, u64 pre_add, u64 post_add, u64 *out) {
+    PbsArgs a{};
+    a.lwe_in = in; a.bsk = ctx->bsk_f; a.tw = ctx->tw; a.lut = lut; a.out = out;
+    a.in_scale = in_scale; a.pre_add_body = pre_add; a.post_add = post_add; a.lwe_dim = ctx->n; a.count = count;
+    CU(launch_pbs(ctx->k, pick_G(ctx->k, count), ctx->p.pbs_base_log, ctx->p.pbs_level, a, ctx->stream));
+    ctx->launches++;
+    return TFA_OK;
+}
+
+// SURVEY §9.4(1), general form.  out [count][nbits][n+1] with bit 0 = least significant extracted bit
+// (the reference's list stores the same ciphertexts in reverse order, many_wopbs.rs:179).
+int dev_extract_bits(tfa_ctx *ctx, const u64 *in, int count, int delta_log, int nbits, u64 *out) {
+    const int np = ctx->n + 1, lw = ctx->lw;
+    if (nbits == 1 && 64 - delta_log - 1 == 0) return dev_keyswitch(ctx, in, count, out);  // the reference's case: KS only
+    WS(buf, u64, (size_t)count * lw);
+    WS(shifted, u64, (size_t)count * lw);
+    WS(ks, u64, (size_t)count * np);
+    WS(pbs, u64, (size_t)count * lw);
+    WS(lut, u64, ctx->N);
+    CU(cudaMemcpyAsync(buf, in, (size_t)count * lw * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    for (int bit = 0; bit < nbits; bit++) {
+        CU(launch_scale_lwe(buf, shifted, (long)count * lw, 1ull << (64 - delta_log - bit - 1), ctx->stream));
+        RC(dev_keyswitch(ctx, shifted, count, ks));
+        CU(cudaMemcpy2DAsync(out + (size_t)bit * np, (size_t)nbits * np * 8, ks, (size_t)np * 8, (size_t)np * 8, count,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->launches += 1;
+        if (bit == nbits - 1) break;
+        CU(launch_fill_u64(lut, ctx->N, (u64)0 - (1ull << (delta_log - 1 + bit)), ctx->stream));
+        RC(dev_pbs(ctx, ks, count, lut, 1, 1ull << 62, 1ull << (delta_log + bit - 1), pbs));
+        CU(launch_sub_lwe(buf, pbs, (long)count * lw, ctx->stream));
+        ctx->launches += 2;
+    }
+    return TFA_OK;
+}
+
+// ggsw_std [count][cbs_level][k+1][gsz]
+int dev_circuit_bootstrap(tfa_ctx *ctx, const u64 *lwe_small, int count, u64 *ggsw_std) {
+    const int kp1 = ctx->k + 1, L = ctx->p.cbs_level;
+    WS(bs, u64, (size_t)count * ctx->lw);
+    WS(lut, u64, (size_t)ctx->N * L);
+    for (int lvl = 1; lvl <= L; lvl++) {
+        const u64 alpha = 1ull << (63 - ctx->p.cbs_base_log * lvl);
+        u64 *l = lut + (size_t)(lvl - 1) * ctx->N;
+        CU(launch_fill_u64(l, ctx->N, (u64)0 - alpha, ctx->stream));
+        ctx->launches++;
+        // homomorphic_shift_boolean with DeltaLog(63): multiply by 2^(64-63-1) = 1, add q/4, PBS, add alpha
+        RC(dev_pbs(ctx, lwe_small, count, l, 1, 1ull << 62, alpha, bs));
+        RC(dev_pfks(ctx, bs, count, ggsw_std + (size_t)(lvl - 1) * kp1 * ctx->gsz, L * kp1 * ctx->gsz));
+    }
+    return TFA_OK;
+}
+
+// SURVEY §9.4(7).  ggsw_f [njobs][nbits][...] with bit 0 = LSB.  LUT polynomials per output:
+// lut[job*lut_job_stride + o*lut_out_stride + poly*N + j], lut_size/N polynomials each.
+int dev_vertical_packing(tfa_ctx *ctx, const double2 *ggsw_f, int njobs, int nbits, const u64 *lut, size_t lut_job_stride,
+                         size_t lut_out_stride, int nouts, int lut_size, u64 *out) {
+    const int npoly = lut_size / ctx->N;
+    int tree = ilog2u(npoly);
+    if (tree > nbits) tree = 0;
+    const u64 *glwe_init = nullptr;
+    const int K = ctx->k;
+    if (tree > 0) {
+        // CMux tree over the `tree` most significant bits: layer by layer, least significant tree bit first
+        const int nleaf = 1 << tree;
+        WS(bufa, u64, (size_t)njobs * nouts * nleaf * ctx->gsz);
+        WS(bufb, u64, (size_t)njobs * nouts * (nleaf / 2) * ctx->gsz);
+        CU(launch_tree_leaves(lut, lut_job_stride, lut_out_stride, njobs, nouts, nleaf, K, bufa, ctx->stream));
+        ctx->launches++;
+        u64 *src = bufa, *dst = bufb;
+        int cnt = nleaf;
+        for (int layer = 0; layer < tree; layer++, cnt >>= 1) {
+            TreeArgs t{};
+            t.ggsw_f = ggsw_f; t.tw = ctx->tw; t.in = src; t.out = dst; t.nbits = nbits; t.bit_index = nbits - tree + layer;
+            t.npairs = nouts * cnt / 2; t.njobs = njobs;
+            int G = (K == 4) ? (t.npairs >= 3 ? 3 : 1) : (t.npairs >= 8 ? 8 : 1);
+            CU(launch_cmux_tree(K, G, ctx->p.cbs_base_log, ctx->p.cbs_level, t, ctx->stream));
+            ctx->launches++;
+            u64 *tmp = src; src = dst; dst = tmp;
+        }
+        glwe_init = src;
+    }
+    VpArgs v{};
+    v.ggsw_f = ggsw_f; v.tw = ctx->tw; v.lut = lut; v.glwe_init = glwe_init; v.out = out;
+    v.lut_job_stride = lut_job_stride; v.lut_out_stride = lut_out_stride;
+    v.nbits = nbits; v.nrot = nbits - tree; v.nouts = nouts; v.njobs = njobs;
+    int G;
+    if (K == 4) G = nouts >= 3 ? 3 : (nouts == 2 ? 2 : 1);
+    else G = nouts >= 8 ? 8 : (nouts >= 4 ? 4 : 1);
+    CU(launch_vp(K, G, ctx->p.cbs_base_log, ctx->p.cbs_level, v, ctx->stream));
+    ctx->launches++;
+    return TFA_OK;
+}
+
+size_t many_wopbs_scratch(const tfa_ctx *ctx, int nct, int nblocks, int nouts, int lut_size) {
+    const int bpb = ilog2u((u64)ctx->p.message_modulus * ctx->p.carry_modulus);
+    const size_t nb = (size_t)nct * nblocks * bpb;  // bits
+    const size_t ggsw = (size_t)ctx->p.cbs_level * (ctx->k + 1) * ctx->gsz * 8;
+    size_t s = 0;
+    s += nb * (ctx->n + 1) * 8;                                 // extracted bits
+    s += nb * ggsw * 2;                                          // ggsw std + fourier
+    s += nb * ctx->lw * 8 * 4;                                   // pbs out, extract_bits buffers
+    s += nb * (size_t)(ctx->big + 1) * ctx->p.pfks_level * 2;    // pfks digits
+    s += nb * (size_t)ctx->big * ctx->p.ks_level * 2;            // ks digits
+    const int npoly = lut_size / ctx->N;
+    if (npoly > 1) s += (size_t)nct * nouts * npoly * ctx->gsz * 8 * 3 / 2;
+    return s + (64 << 10) * 16;
+}
+
+// many_wopbs_without_padding (many_wopbs.rs:31-116) for nct radix ciphertexts of nblocks blocks.
+// out [nct][nouts][lw].
+int dev_many_wopbs(tfa_ctx *ctx, const u64 *ct_in, int nct, int nblocks, const u64 *lut, size_t lut_job_stride,
+                   size_t lut_out_stride, int nouts, int lut_size, u64 *out) {
+    const int block_mod = ctx->p.message_modulus * ctx->p.carry_modulus;
+    const int bpb = ilog2u(block_mod);
+    const int delta_log = ilog2u((1ull << 63) / (block_mod / 2));
+    const int nbits = nblocks * bpb;               // selector bits per ciphertext
+    const int nb = nct * nbits;
+    // (1) custom_extract_bits (many_wopbs.rs:161-202): every block independently
+    WS(bits, u64, (size_t)nb * (ctx->n + 1));
+    RC(dev_extract_bits(ctx, ct_in, nct * nblocks, delta_log, bpb, bits));
+    // (2) circuit bootstrap every bit (many_wopbs.rs:252-264) and move the GGSWs to the Fourier domain
+    const size_t ggsw_words = (size_t)ctx->p.cbs_level * (ctx->k + 1) * ctx->gsz;
+    WS(ggsw_std, u64, (size_t)nb * ggsw_words);
+    WS(ggsw_f, double2, (size_t)nb * ggsw_words / 2);
+    RC(dev_circuit_bootstrap(ctx, bits, nb, ggsw_std));
+    RC(dev_fourier(ctx, ggsw_std, (long)nb * ctx->p.cbs_level * (ctx->k + 1) * (ctx->k + 1), ggsw_f));
+    // (3) one vertical packing per LUT output (many_wopbs.rs:267-279)
+    return dev_vertical_packing(ctx, ggsw_f, nct, nbits, lut, lut_job_stride, lut_out_stride, nouts, lut_size, out);
+}
+
+int dev_lwe_sum(tfa_ctx *ctx, const std::vector<SumEntry> &entries, int unit_words) {
+    WS(d, SumEntry, entries.size());
+    CU(cudaMemcpyAsync(d, entries.data(), entries.size() * sizeof(SumEntry), cudaMemcpyHostToDevice, ctx->stream));
+    // the host vector may die right after this call: make the copy complete (pageable source => staged synchronously)
+    CU(launch_lwe_sum(d, (int)entries.size(), unit_words, ctx->stream));
+    ctx->launches++;
+    return TFA_OK;
+}

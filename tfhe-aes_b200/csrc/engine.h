@@ -1,0 +1,86 @@
+// engine.h — internal context of the library (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/tfhe_aes_b200.h"
+#include "kernels.h"
+
+typedef uint64_t u64;
+
+struct tfa_ctx {
+    tfa_params p;
+    int n, k, N, big, lw, gsz;  // lw = k*N+1 words per big LWE, gsz = (k+1)*N words per GLWE
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    std::string err;
+    std::mutex mu;
+    u64 launches;
+
+    // prepared keys (device)
+    double2 *bsk_f;        // [n][pbs_level][k+1][256][k+1]
+    u64 *ksk;              // [big*ks_level][ks_cols_pad]
+    u64 *pfpksk;           // [k+1][(big+1)*pfks_level][gsz]
+    u64 *ksk_colsum;       // [ks_cols_pad]
+    u64 *pfpksk_colsum;    // [(k+1)*gsz]
+    double2 *tw;           // 512 twiddles
+    int ks_cols_pad;
+    bool keys_allocated, keys_ready;
+
+    // client-side secrets (tfa_client_keygen only)
+    u64 *d_lwe_sk, *d_glwe_sk;
+    std::vector<u64> h_lwe_sk, h_glwe_sk;
+
+    // cached device LUT sets (sbox module): [0]=S [1]={S,2S,3S} [2]=invS [3]={9,11,13,14}x [4]=identity
+    u64 *lut_cache[5];
+
+    // bump workspace
+    char *ws;
+    size_t ws_cap, ws_off;
+
+    size_t bsk_f_bytes() const { return (size_t)n * p.pbs_level * (k + 1) * 256 * (k + 1) * sizeof(double2); }
+    size_t ksk_bytes() const { return (size_t)big * p.ks_level * ks_cols_pad * 8; }
+    size_t pfpksk_bytes() const { return (size_t)(k + 1) * (big + 1) * p.pfks_level * gsz * 8; }
+    size_t byte_words() const { return (size_t)8 * lw; }
+
+    int fail(int code, const std::string &what) { err = what; return code; }
+    int fail_cuda(const char *what, cudaError_t e) {
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return TFA_ERR_CUDA;
+    }
+};
+
+#define CU(call)                                                       \
+    do {                                                               \
+        cudaError_t e__ = (call);                                      \
+        if (e__ != cudaSuccess) return ctx->fail_cuda(#call, e__);     \
+    } while (0)
+#define RC(call)                  \
+    do {                          \
+        int r__ = (call);         \
+        if (r__ != TFA_OK) return r__; \
+    } while (0)
+
+// workspace helpers
+int ws_reserve(tfa_ctx *ctx, size_t bytes);      // make sure `bytes` of scratch are available, reset the bump pointer
+void *ws_alloc(tfa_ctx *ctx, size_t bytes);      // bump allocation (256 B aligned); nullptr if exhausted
+template <typename T>
+static inline T *ws_get(tfa_ctx *ctx, size_t count) { return reinterpret_cast<T *>(ws_alloc(ctx, count * sizeof(T))); }
+
+// device-level stages (all asynchronous on ctx->stream, scratch from the workspace)
+int dev_keyswitch(tfa_ctx *ctx, const u64 *in, int count, u64 *out);
+int dev_pbs(tfa_ctx *ctx, const u64 *in, int count, const u64 *lut, u64 in_scale, u64 pre_add, u64 post_add, u64 *out);
+int dev_pfks(tfa_ctx *ctx, const u64 *in, int count, u64 *out, int out_stride);
+int dev_fourier(tfa_ctx *ctx, const u64 *polys, long npoly, double2 *out);
+int dev_extract_bits(tfa_ctx *ctx, const u64 *in, int count, int delta_log, int nbits, u64 *out /* [count][nbits][n+1], 0 = LSB */);
+int dev_circuit_bootstrap(tfa_ctx *ctx, const u64 *lwe_small, int count, u64 *ggsw_std);
+int dev_vertical_packing(tfa_ctx *ctx, const double2 *ggsw_f, int njobs, int nbits, const u64 *lut, size_t lut_job_stride,
+                         size_t lut_out_stride, int nouts, int lut_size, u64 *out);
+int dev_many_wopbs(tfa_ctx *ctx, const u64 *ct_in, int nct, int nblocks, const u64 *lut, size_t lut_job_stride,
+                   size_t lut_out_stride, int nouts, int lut_size, u64 *out);
+size_t many_wopbs_scratch(const tfa_ctx *ctx, int nct, int nblocks, int nouts, int lut_size);
+int dev_lwe_sum(tfa_ctx *ctx, const std::vector<SumEntry> &entries, int unit_words);
+int require_keys(tfa_ctx *ctx);
+const u64 *cached_lut(tfa_ctx *ctx, int which);  // device pointer, see lut_cache

@@ -1,0 +1,134 @@
+// fft_core.cuh — register-level building blocks of the 256-point complex FFT that implements the
+// negacyclic transform for N = 512 (reference call sites many_wopbs.rs:253,263,277).
+//
+// Convention (same as tfhe-fft): z[n] = p[n] + i p[n+256]; X[k] = sum_n z[n] theta^(n(4k+1)),
+// theta = exp(2 pi i / 1024), i.e. twist exp(i pi n / 512) followed by a 256-point DFT with
+// kernel exp(+2 pi i nk / 256).  Pointwise products of such spectra are negacyclic products.
+//
+// Decomposition ("four-step", 16 x 16): n = 16 n1 + n2, k = k1 + 16 k2.
+//   pass 1 (lane n2):  T[k1] = sum_n1 z[16 n1 + n2] phi^(n1) W16^(n1 k1),  phi = exp(2 pi i/64)
+//   mid twiddle:       T[k1] *= theta^(n2 (4 k1 + 1))
+//   exchange through shared memory (16 x 16 transpose inside one half-warp)
+//   pass 2 (lane k1):  X[k1 + 16 k2] = sum_n2 T[k1][n2] W16^(n2 k2)
+// Each of the 16 lanes holds 16 complex values in registers, so a transform costs one shared-memory
+// round trip.  Everything here is __host__ __device__ so the CPU emulation in emu.cu runs the very
+// same code the kernels run.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifndef HD
+#define HD __host__ __device__ __forceinline__
+#endif
+
+typedef double2 cd;
+
+#include "w64_table.inc"
+
+HD cd cmk(double x, double y) { cd r; r.x = x; r.y = y; return r; }
+HD cd cadd(cd a, cd b) { return cmk(a.x + b.x, a.y + b.y); }
+HD cd csub(cd a, cd b) { return cmk(a.x - b.x, a.y - b.y); }
+HD cd cmul(cd a, cd b) { return cmk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// acc += a * b
+HD void cmac(cd &acc, cd a, cd b) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+
+// v * exp(SIGN * 2 pi i m / 64), m a compile-time constant after unrolling
+template <int SIGN>
+HD cd mul_w64(cd v, int m) {
+    m &= 63;
+    if (m == 0) return v;
+    if (m == 16) return SIGN > 0 ? cmk(-v.y, v.x) : cmk(v.y, -v.x);
+    if (m == 32) return cmk(-v.x, -v.y);
+    if (m == 48) return SIGN > 0 ? cmk(v.y, -v.x) : cmk(-v.y, v.x);
+    const double c = w64_cos(m), s = SIGN * w64_sin(m);
+    return cmk(v.x * c - v.y * s, v.x * s + v.y * c);
+}
+
+// radix-4 butterfly, kernel exp(SIGN * 2 pi i /4): (a,b,c,d) -> (y0,y1,y2,y3)
+template <int SIGN>
+HD void radix4(cd &a, cd &b, cd &c, cd &d) {
+    cd t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = csub(b, d);
+    cd it3 = SIGN > 0 ? cmk(-t3.y, t3.x) : cmk(t3.y, -t3.x);
+    a = cadd(t0, t2);
+    c = csub(t0, t2);
+    b = cadd(t1, it3);
+    d = csub(t1, it3);
+}
+
+// position of natural output index k (0..15) inside the register array after fft16
+HD constexpr int rev4(int k) { return ((k & 3) << 2) | (k >> 2); }
+
+// 16-point DFT in registers, kernel exp(SIGN * 2 pi i nk / 16).  In: v[n].  Out: X[k] at v[rev4(k)].
+template <int SIGN>
+HD void fft16(cd (&v)[16]) {
+#pragma unroll
+    for (int n2 = 0; n2 < 4; n2++) radix4<SIGN>(v[n2], v[n2 + 4], v[n2 + 8], v[n2 + 12]);
+#pragma unroll
+    for (int n2 = 1; n2 < 4; n2++)
+#pragma unroll
+        for (int k1 = 1; k1 < 4; k1++) v[n2 + 4 * k1] = mul_w64<SIGN>(v[n2 + 4 * k1], 4 * n2 * k1);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) radix4<SIGN>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+}
+
+// Exchange buffer of one 16-lane group: 16 rows of 17 complex (one pad element per row keeps the
+// transposed reads at two wavefronts per half-warp).  The same storage, read linearly as 256
+// complex, is also the hand-over format to / from the multiply-accumulate phase.
+#define XB_STRIDE 17
+#define XB_ELEMS (16 * XB_STRIDE)
+
+// Mid-twiddle tables (filled once per CTA): twf[k1*16 + n2] = theta^(n2 (4 k1 + 1)),
+// twi[n2*16 + k1] = conj of the same value.
+HD void fft256_fwd_pass1(cd (&v)[16], int lane, const cd *twf, cd *xb) {
+#pragma unroll
+    for (int n1 = 1; n1 < 16; n1++) v[n1] = mul_w64<1>(v[n1], n1);
+    fft16<1>(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) xb[k1 * XB_STRIDE + lane] = cmul(v[rev4(k1)], twf[k1 * 16 + lane]);
+}
+// lane = k1.  Out: X[lane + 16 k2] at v[rev4(k2)]
+HD void fft256_fwd_pass2(cd (&v)[16], int lane, const cd *xb) {
+#pragma unroll
+    for (int n2 = 0; n2 < 16; n2++) v[n2] = xb[lane * XB_STRIDE + n2];
+    fft16<1>(v);
+}
+// lane = k1.  In: v[k2] = X[lane + 16 k2].  Writes twiddled U[n2] to xb[n2][lane].
+HD void fft256_inv_pass1_compute(cd (&v)[16]) { fft16<-1>(v); }
+HD void fft256_inv_pass1_store(cd (&v)[16], int lane, const cd *twi, cd *xb) {
+#pragma unroll
+    for (int n2 = 0; n2 < 16; n2++) xb[n2 * XB_STRIDE + lane] = cmul(v[rev4(n2)], twi[n2 * 16 + lane]);
+}
+// lane = n2.  Out: z[16 n1 + lane] * 256 at v[rev4(n1)] before the final untwist; this applies the
+// untwist conj(phi^n1) and the 1/256 scale and returns natural order in v[n1].
+HD void fft256_inv_pass2(cd (&v)[16], int lane, const cd *xb) {
+    cd t[16];
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) t[k1] = xb[lane * XB_STRIDE + k1];
+    fft16<-1>(t);
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) {
+        cd u = mul_w64<-1>(t[rev4(n1)], n1);
+        v[n1] = cmk(u.x * (1.0 / 256.0), u.y * (1.0 / 256.0));
+    }
+}
+
+// round-to-nearest f64 -> u64 modulo 2^64 (SURVEY §9.6 "round to nearest, reduce mod 2^64")
+HD uint64_t f64_to_torus(double v) {
+    double q = v * (1.0 / 18446744073709551616.0);
+#ifdef __CUDA_ARCH__
+    double r = fma(-18446744073709551616.0, rint(q), v);
+    double rr = rint(r);
+    if (rr >= 9223372036854775808.0) rr -= 18446744073709551616.0;
+    return (uint64_t)__double2ll_rn(rr);
+#else
+    double r = v - 18446744073709551616.0 * __builtin_nearbyint(q);
+    double rr = __builtin_nearbyint(r);
+    if (rr >= 9223372036854775808.0) rr -= 18446744073709551616.0;
+    return (uint64_t)(int64_t)rr;
+#endif
+}

@@ -1,0 +1,93 @@
+// kernels.h — argument blocks and host launchers of the sm_100a kernels (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct PbsArgs {
+    const uint64_t *lwe_in;   // [count][lwe_dim+1]
+    const double2 *bsk;       // Fourier BSK [lwe_dim][level][row][p][col]
+    const double2 *tw;        // 512 twiddles (make_twiddle_tables)
+    const uint64_t *lut;      // [N] body of the trivial accumulator
+    uint64_t *out;            // [count][k*N+1]
+    uint64_t in_scale;        // cleartext multiplier applied to the input before the modulus switch
+    uint64_t pre_add_body;    // added to the input body before the modulus switch (q/4 centring)
+    uint64_t post_add;        // added to the output body
+    int lwe_dim;
+    int count;
+};
+struct VpArgs {
+    const double2 *ggsw_f;    // [njobs][nbits][level][row][p][col], bit 0 = LSB
+    const double2 *tw;
+    const uint64_t *lut;      // [.. job*lut_job_stride + out*lut_out_stride + j ..] LUT polynomial per output (if glwe_init == 0)
+    const uint64_t *glwe_init;// or [njobs][nouts][(k+1)N] start accumulators (root of the CMux tree)
+    uint64_t *out;            // [njobs][nouts][k*N+1]
+    size_t lut_job_stride;
+    size_t lut_out_stride;
+    int nbits;                // GGSWs per job
+    int nrot;                 // GGSWs consumed by the blind rotation (bits 0..nrot-1)
+    int nouts;
+    int njobs;
+};
+struct TreeArgs {
+    const double2 *ggsw_f;    // [njobs][nbits][...]
+    const double2 *tw;
+    const uint64_t *in;       // [njobs][2*npairs][(k+1)N]
+    uint64_t *out;            // [njobs][npairs][(k+1)N]
+    int nbits;
+    int bit_index;            // which GGSW of the job drives this layer
+    int npairs;
+    int njobs;
+};
+struct ConvertArgs {
+    const uint64_t *in;       // [npoly][N], polys ordered [g][level][row][col]
+    double2 *out;             // [g][level][row][p][col]
+    const double2 *tw;
+    long npoly;
+    int glwe_dim;
+};
+struct GemvArgs {
+    const uint16_t *digits;   // [count][rows] offset digits u = d + beta/2
+    const uint64_t *key;      // [nkeys][rows][ncols]
+    uint64_t *out;            // [count][nkeys*ncols (+pad)]
+    size_t key_stride;        // words between keys
+    int key_row_stride;       // words between key rows (>= ncols, even)
+    int out_stride;           // words between ciphertexts in out
+    int rows;
+    int ncols;
+    int nkeys;
+    int count;
+    int rows_per_split;
+};
+
+cudaError_t launch_pbs(int K, int G, int base_log, int levels, const PbsArgs &a, cudaStream_t s);
+cudaError_t launch_vp(int K, int G, int base_log, int levels, const VpArgs &a, cudaStream_t s);
+cudaError_t launch_cmux_tree(int K, int G, int base_log, int levels, const TreeArgs &a, cudaStream_t s);
+cudaError_t launch_fourier_convert(const ConvertArgs &a, cudaStream_t s);
+
+// integer kernels (int_kernels.cu)
+cudaError_t launch_decompose(const uint64_t *in, int in_stride, int nelem, int count, int base_log, int levels,
+                             uint16_t *digits, cudaStream_t s);
+cudaError_t launch_gemv(const GemvArgs &a, cudaStream_t s);
+cudaError_t launch_key_colsum(const uint64_t *key, int rows, int ncols, int row_stride, int nkeys, size_t key_stride,
+                              uint64_t *sums, cudaStream_t s);
+// out[b][c] = offset*colsum[c] (+ body of in for the keyswitch when body_src != nullptr)
+cudaError_t launch_gemv_init(uint64_t *out, int out_stride, int total_cols, int count, const uint64_t *colsum,
+                             uint64_t offset, const uint64_t *body_src, int body_src_stride, int body_src_index,
+                             int body_dst_col, cudaStream_t s);
+struct SumEntry {
+    const uint64_t *src[5];
+    uint64_t *dst;
+    int nsrc;
+    int _pad;
+};
+cudaError_t launch_lwe_sum(const SumEntry *entries, int nentries, int unit_words, cudaStream_t s);
+cudaError_t launch_scale_lwe(const uint64_t *in, uint64_t *out, long nwords, uint64_t mul, cudaStream_t s);
+cudaError_t launch_sub_lwe(uint64_t *inout, const uint64_t *sub, long nwords, cudaStream_t s);
+cudaError_t launch_add_body(uint64_t *lwe, int lwe_words, int count, uint64_t add, cudaStream_t s);
+cudaError_t launch_fill_u64(uint64_t *dst, long n, uint64_t v, cudaStream_t s);
+// trivial GLWE leaves for the CMux tree: out[job][out][leaf][(k+1)N] from lut[job*js + out*os + leaf*N + j]
+cudaError_t launch_tree_leaves(const uint64_t *lut, size_t lut_job_stride, size_t lut_out_stride, int njobs, int nouts,
+                               int nleaf, int glwe_dim, uint64_t *out, cudaStream_t s);
+// counter-add LUTs of Server::add_scalar (server.rs:181-248), generated on the device
+cudaError_t launch_add_scalar_luts(const uint64_t *counters_lo_hi, int nblk, int byte_index, int nbits, uint64_t *luts,
+                                   cudaStream_t s);
