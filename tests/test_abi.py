@@ -1,0 +1,78 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads, exports every symbol declared in
+include/tfhe_aes_b200.h, the host-only entry points work, and compute entry points fail loudly
+(no CPU fallback) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "tfhe_aes_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tfa_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg.load_library()
+    names = declared_symbols()
+    assert len(names) >= 45
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/tfhe_aes_b200.h but not exported"
+    for n in ("tfa_aes_key_expansion", "tfa_aes_encrypt", "tfa_aes_decrypt", "tfa_aes_encryption", "tfa_aes_decryption",
+              "tfa_add_scalar", "tfa_many_wopbs", "tfa_sbox", "tfa_many_sbox", "tfa_gen_lut"):
+        assert n in names
+
+
+def test_param_opt_matches_reference(pkg):
+    lib = pkg.load_library()
+    p = pkg.Params()
+    lib.tfa_param_opt(C.byref(p))
+    ref = pkg.param_opt()
+    for f, _ in pkg.Params._fields_:
+        assert getattr(p, f) == getattr(ref, f)
+    # client.rs:31-57
+    assert (p.lwe_dim, p.glwe_dim, p.poly_size) == (669, 4, 512)
+    assert (p.pbs_base_log, p.pbs_level, p.ks_base_log, p.ks_level) == (8, 5, 2, 6)
+    assert (p.pfks_base_log, p.pfks_level, p.cbs_base_log, p.cbs_level) == (12, 3, 15, 1)
+    assert (p.message_modulus, p.carry_modulus) == (2, 1)
+
+
+def test_gen_lut_host_entry_point(pkg):
+    p = pkg.param_opt()
+    assert pkg.lut_size(p, 8) == 512 and pkg.lut_size(p, 9) == 512 and pkg.lut_size(p, 10) == 1024
+    lut = pkg.gen_lut(p, 8, lambda x: pkg.SBOX[x])
+    assert lut.shape == (8, 512)
+    for j in range(8):
+        assert np.array_equal(lut[j, :256] >> np.uint64(63), np.array([(pkg.SBOX[x] >> j) & 1 for x in range(256)], dtype=np.uint64))
+    assert np.all((lut & np.uint64((1 << 63) - 1)) == 0)
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a CUDA device the context cannot be created: the product never computes on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.TfaError) as ei:
+        pkg.Engine(pkg.param_opt())
+    assert ei.value.code == 2  # TFA_ERR_CUDA
+
+
+def test_unsupported_parameters_are_rejected(pkg):
+    p = pkg.param_opt()
+    p.poly_size = 1024
+    with pytest.raises(pkg.TfaError) as ei:
+        pkg.Engine(p)
+    assert ei.value.code == 1  # TFA_ERR_PARAM
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "tfhe-aes_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) and "emu" not in f:
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "tfhe_oracle" not in txt and "import orc" not in txt, f

@@ -1,7 +1,9 @@
 """GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on identical
 keys and inputs.  Integer stages (keyswitch, PFKS, linear layers) must be bit-exact.  FP64 stages
-(PBS, circuit bootstrap, vertical packing) are compared on the torus with the tolerance written in
-each test, and always on the decrypted plaintext (exact)."""
+(PBS, circuit bootstrap, vertical packing) are compared on the PHASE (b - <a, s>, i.e. message +
+noise) with the tolerance written in each test, and always on the decrypted plaintext (exact).
+Raw ciphertext words of a multi-step FP64 stage are not comparable: an FFT rounding difference of
+one unit in the last decomposition digit replaces the mask by a different, equally valid one."""
 import numpy as np
 import pytest
 
@@ -74,8 +76,9 @@ def test_bootstrap_matches_oracle(engine_test, oracle_test):
     lwe = o.encrypt_lwe_small((msgs << np.uint64(63)) + np.uint64(1 << 62))
     lut = np.full(512, (1 << 64) - (1 << 48), dtype=np.uint64)  # the CBS accumulator (-2^48 everywhere)
     got, ref = engine_test.bootstrap(lwe, lut), o.bootstrap(lwe, lut)
-    # tolerance 2^34: n=24 CMux steps each differ by FFT rounding (~2^26)
-    assert torus_absdiff(got, ref) < 2 ** 34
+    # tolerance 2^36 on the phase: both sides carry the PBS noise (decomposition rounding 2^24 * sqrt(kN/2)
+    # per step plus FFT rounding ~2^26), payload is 2^48
+    assert torus_absdiff(o.phase_big(got), o.phase_big(ref)) < 2 ** 36
     ph = o.phase_big(got) + np.uint64(1 << 48)
     assert np.array_equal(((ph + np.uint64(1 << 48)) >> np.uint64(49)) & np.uint64(1), msgs)
 
@@ -85,7 +88,7 @@ def test_bootstrap_general_lut(engine_test, oracle_test):
     o = oracle_test
     lut = rng.integers(0, 2 ** 64, 512, dtype=np.uint64)
     lwe = o.encrypt_lwe_small(rng.integers(0, 2 ** 64, 13, dtype=np.uint64))
-    assert torus_absdiff(engine_test.bootstrap(lwe, lut), o.bootstrap(lwe, lut)) < 2 ** 34
+    assert torus_absdiff(o.phase_big(engine_test.bootstrap(lwe, lut)), o.phase_big(o.bootstrap(lwe, lut))) < 2 ** 36
 
 
 def test_extract_bits_reference_case_is_keyswitch(engine_test, oracle_test):
@@ -110,7 +113,8 @@ def test_extract_bits_general_pbs_loop(engine_test2, oracle_test2):
     for i, v in enumerate(vals):
         ref = o.extract_bits(ct[i], 62, 2)
         assert np.array_equal(got[i, 1], ref[1])            # first extracted (LSB): keyswitch only, bit exact
-        assert torus_absdiff(got[i, 0], ref[0]) < 2 ** 40   # second goes through a PBS (FP64) and a keyswitch
+        # second bit goes through a PBS (FP64) and a keyswitch (rounds below 2^52): compare phases
+        assert torus_absdiff(o.phase_small(got[i, 0]), o.phase_small(ref[0])) < 2 ** 58
         ph = o.phase_small(got[i])
         dec = ((ph + np.uint64(1 << 62)) >> np.uint64(63)) & np.uint64(1)
         assert int(dec[0]) == (int(v) >> 1) and int(dec[1]) == (int(v) & 1)
@@ -122,9 +126,9 @@ def test_circuit_bootstrap_matches_oracle(engine_test, oracle_test):
     got = engine_test.circuit_bootstrap(lwe)
     for i in range(3):
         ref = o.circuit_bootstrap_boolean(lwe[i])
-        # PFKS is exact given its input; the input (PBS output) differs by < 2^34, amplified by at most
-        # sum |digit| <= (kN+1) * 3 * 2^11 on the dropped bits -> well below 2^48
-        assert torus_absdiff(got[i], ref) < 2 ** 48
+        # every GGSW row is a GLWE of (-S_r or 1) * m * 2^49: compare the phases, tolerance 2^40
+        # (PBS noise ~2^31 plus PFKS rounding below 2^28 over kN+1 terms)
+        assert torus_absdiff(o.glwe_phase(got[i]), o.glwe_phase(ref)) < 2 ** 40
 
 
 def test_vertical_packing_matches_oracle(engine_test, oracle_test):
@@ -137,7 +141,7 @@ def test_vertical_packing_matches_oracle(engine_test, oracle_test):
     got = engine_test.vertical_packing(lut, ggsw)
     for j in range(5):
         ref = o.vertical_packing(lut[j], ggsw)
-        assert torus_absdiff(got[j], ref) < 2 ** 50
+        assert torus_absdiff(o.phase_big(got[j]), o.phase_big(ref)) < 2 ** 54  # level-1 product: noise ~2^51 per step
     dec = o.decrypt_bits(got)
     assert np.array_equal(dec, (lut[:, 0, 0xB2] >> np.uint64(63)).astype(np.uint8))
 
@@ -153,7 +157,7 @@ def test_vertical_packing_cmux_tree(engine_test, oracle_test):
     lut = rng.integers(0, 2, (3, 2, 512)).astype(np.uint64) << np.uint64(63)
     got = engine_test.vertical_packing(lut, ggsw)
     for j in range(3):
-        assert torus_absdiff(got[j], o.vertical_packing(lut[j], ggsw)) < 2 ** 50
+        assert torus_absdiff(o.phase_big(got[j]), o.phase_big(o.vertical_packing(lut[j], ggsw))) < 2 ** 54
     dec = o.decrypt_bits(got)
     assert np.array_equal(dec, (lut.reshape(3, 1024)[:, value] >> np.uint64(63)).astype(np.uint8))
     # 11 bits -> 4 polynomials -> depth 2
@@ -165,7 +169,7 @@ def test_vertical_packing_cmux_tree(engine_test, oracle_test):
     got = engine_test.vertical_packing(lut, ggsw)
     assert np.array_equal(o.decrypt_bits(got), (lut.reshape(2, 2048)[:, value] >> np.uint64(63)).astype(np.uint8))
     for j in range(2):
-        assert torus_absdiff(got[j], o.vertical_packing(lut[j], ggsw)) < 2 ** 50
+        assert torus_absdiff(o.phase_big(got[j]), o.phase_big(o.vertical_packing(lut[j], ggsw))) < 2 ** 54
 
 
 # ---- sbox module ------------------------------------------------------------------------------------------
@@ -179,7 +183,7 @@ def test_many_wopbs_matches_oracle(pkg, engine_test, oracle_test):
     got = engine_test.many_wopbs(ct, luts)
     for i, b in enumerate(data):
         ref = o.many_wopbs(ct[i], luts)
-        assert torus_absdiff(got[i], ref) < 2 ** 58  # decision threshold is 2^62; noise itself is ~2^53
+        assert torus_absdiff(o.phase_big(got[i]), o.phase_big(ref)) < 2 ** 58  # decision threshold 2^62; noise ~2^53
         s = pkg.SBOX[b]
         assert o.decrypt_bytes(got[i]) == bytes([s, pkg.mul2(s), pkg.mul3(s)])
 
@@ -249,7 +253,7 @@ def test_key_expansion_encrypt_decrypt_kat(pkg, engine_test, oracle_test, orc):
         assert o.decrypt_bytes(dec[i]) == PT[i]
     # ciphertext-level agreement with the oracle on one block (tolerance as in test_many_wopbs)
     ref = o.aes_encrypt(rk, states[0])
-    assert torus_absdiff(enc[0], ref) < 2 ** 59
+    assert torus_absdiff(o.phase_big(enc[0]), o.phase_big(ref)) < 2 ** 59
 
 
 def test_add_scalar_and_ctr(pkg, engine_test, oracle_test, orc):
@@ -304,7 +308,7 @@ def test_opt_bootstrap_matches_oracle(engine_opt, oracle_opt):
     lut = np.full(512, (1 << 64) - (1 << 48), dtype=np.uint64)
     got, ref = engine_opt.bootstrap(ks, lut), o.bootstrap(ks, lut)
     # 669 CMux steps, FFT rounding ~2^26 each -> random walk ~2^31; bound 2^36
-    assert torus_absdiff(got, ref) < 2 ** 36
+    assert torus_absdiff(o.phase_big(got), o.phase_big(ref)) < 2 ** 36
     ph = o.phase_big(got) + np.uint64(1 << 48)
     assert np.array_equal(((ph + np.uint64(1 << 48)) >> np.uint64(49)) & np.uint64(1), msgs)
 
@@ -326,7 +330,7 @@ def test_opt_many_sbox_noise_within_tolerance(pkg, engine_opt, oracle_opt):
         ref = o.many_sbox(ct[i], False)
         errs_o.append(o.decrypt_bits(ref, with_err=True)[1])
         if i < 4:
-            assert torus_absdiff(got[i], ref) < 2 ** 58
+            assert torus_absdiff(o.phase_big(got[i]), o.phase_big(ref)) < 2 ** 58
     vg = np.var(np.concatenate(errs_g).astype(np.float64))
     vo = np.var(np.concatenate(errs_o).astype(np.float64))
     assert len(np.concatenate(errs_g)) >= 1000
