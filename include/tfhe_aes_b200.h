@@ -69,6 +69,12 @@ int tfa_ctx_alloc_keys(tfa_ctx *ctx);
 int tfa_ctx_key_buffers(tfa_ctx *ctx, void **dev_ptrs /* [8] */, size_t *bytes /* [8] */, int *count);
 int tfa_ctx_keys_ready(tfa_ctx *ctx);
 int tfa_ctx_synchronize(tfa_ctx *ctx);
+/* per-stage GPU time of everything launched since tfa_ctx_profile(ctx, 1): stages are
+ * 0 ks_decompose 1 ks_gemv 2 pbs 3 pfks_decompose 4 pfks_gemv 5 fourier 6 vp 7 cmux_tree 8 linear 9 misc */
+int tfa_ctx_profile(tfa_ctx *ctx, int enable);
+int tfa_ctx_profile_report(tfa_ctx *ctx, double *ms_per_stage /* [10] */, int *launch_groups /* [10] */);
+/* DFMA microbenchmark: measured FP64 pipe peak of the device in TFLOP/s (roofline denominator) */
+int tfa_measure_fp64_peak(tfa_ctx *ctx, double *tflops);
 /* number of kernels this library launched on the context since creation (bench.py's gpu_launches) */
 uint64_t tfa_ctx_launch_count(const tfa_ctx *ctx);
 
@@ -125,6 +131,8 @@ int tfa_aes_key_expansion_dev(tfa_ctx *ctx, const uint64_t *key_ct, const uint64
 int tfa_keyswitch(tfa_ctx *ctx, const uint64_t *in, int count, uint64_t *out);
 /* programmable bootstrap with accumulator body `lut` [N]: in [count][n+1] -> out [count][lw] */
 int tfa_bootstrap(tfa_ctx *ctx, const uint64_t *in, int count, const uint64_t *lut, uint64_t *out);
+int tfa_bootstrap_dev(tfa_ctx *ctx, const uint64_t *in, int count, const uint64_t *lut, uint64_t pre_add_body,
+                      uint64_t post_add_body, uint64_t *out);
 /* extract_bits (many_wopbs.rs:194-199): in [count][lw] -> out [count][nbits][n+1], index 0 = MSB */
 int tfa_extract_bits(tfa_ctx *ctx, const uint64_t *in, int count, int delta_log, int nbits, uint64_t *out);
 /* PFKS with key `key_index` (inside circuit_bootstrap_boolean): in [count][lw] -> out [count][(k+1)N] */
@@ -144,6 +152,7 @@ int tfa_client_encrypt_bytes(tfa_ctx *ctx, const uint8_t *bytes, int count, uint
 int tfa_client_decrypt_bytes(tfa_ctx *ctx, const uint64_t *ct, int count, uint8_t *bytes_out);
 int tfa_client_encrypt_bytes_dev(tfa_ctx *ctx, const uint8_t *bytes_host, int count, uint64_t seed, uint64_t *out_dev);
 int tfa_client_decrypt_bytes_dev(tfa_ctx *ctx, const uint64_t *ct_dev, int count, uint8_t *bytes_out_host);
+int tfa_client_set_secret_keys(tfa_ctx *ctx, const uint64_t *lwe_sk, const uint64_t *glwe_sk);
 /* secret keys (host copies) so a test can cross-check generated keys with an independent implementation */
 int tfa_client_secret_keys(tfa_ctx *ctx, uint64_t *lwe_sk /* [n] */, uint64_t *glwe_sk /* [k*N] */);
 

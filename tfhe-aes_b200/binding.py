@@ -85,6 +85,11 @@ _SIGS = {
     "tfa_client_decrypt_bytes_dev": [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p],
     "tfa_client_secret_keys": [C.c_void_p, C.c_void_p, C.c_void_p],
     "tfa_gen_lut": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p],
+    "tfa_bootstrap_dev": [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p],
+    "tfa_client_set_secret_keys": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "tfa_ctx_profile": [C.c_void_p, C.c_int],
+    "tfa_ctx_profile_report": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "tfa_measure_fp64_peak": [C.c_void_p, C.POINTER(C.c_double)],
     "tfa_lut_size": [C.c_void_p, C.c_int],
 }
 
@@ -220,6 +225,46 @@ class Engine:
 
     def synchronize(self):
         self._ck(self.lib.tfa_ctx_synchronize(self.h))
+
+    STAGES = ("ks_decompose", "ks_gemv", "pbs", "pfks_decompose", "pfks_gemv", "fourier", "vp", "cmux_tree", "linear", "misc")
+
+    def profile(self, enable=True):
+        self._ck(self.lib.tfa_ctx_profile(self.h, int(enable)))
+
+    def profile_report(self):
+        ms = np.zeros(10, dtype=np.float64)
+        cnt = np.zeros(10, dtype=np.int32)
+        self._ck(self.lib.tfa_ctx_profile_report(self.h, _p(ms), _p(cnt)))
+        return {n: (float(ms[i]), int(cnt[i])) for i, n in enumerate(self.STAGES) if cnt[i]}
+
+    def measure_fp64_peak(self):
+        v = C.c_double()
+        self._ck(self.lib.tfa_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value
+
+    # device-pointer calls (ints are raw device addresses, e.g. torch.Tensor.data_ptr())
+    def bootstrap_dev(self, in_ptr, count, lut_ptr, pre_add, post_add, out_ptr):
+        self._ck(self.lib.tfa_bootstrap_dev(self.h, C.c_void_p(in_ptr), count, C.c_void_p(lut_ptr), pre_add, post_add, C.c_void_p(out_ptr)))
+
+    def aes_ctr_dev(self, rk_ptr, iv_ptr, first, nblk, out_ptr):
+        self._ck(self.lib.tfa_aes_ctr_dev(self.h, C.c_void_p(rk_ptr), C.c_void_p(iv_ptr), first & (2 ** 64 - 1), first >> 64, nblk, C.c_void_p(out_ptr)))
+
+    def aes_encrypt_dev(self, rk_ptr, st_ptr, nblk):
+        self._ck(self.lib.tfa_aes_encrypt_dev(self.h, C.c_void_p(rk_ptr), C.c_void_p(st_ptr), nblk))
+
+    def aes_decrypt_dev(self, rk_ptr, st_ptr, nblk):
+        self._ck(self.lib.tfa_aes_decrypt_dev(self.h, C.c_void_p(rk_ptr), C.c_void_p(st_ptr), nblk))
+
+    def aes_round_dev(self, rk_ptr, st_ptr, nblk):
+        self._ck(self.lib.tfa_aes_round_dev(self.h, C.c_void_p(rk_ptr), C.c_void_p(st_ptr), nblk))
+
+    def aes_key_expansion_dev(self, key_ptr, rk_ptr, rcon_ptr=None):
+        self._ck(self.lib.tfa_aes_key_expansion_dev(self.h, C.c_void_p(key_ptr), C.c_void_p(rcon_ptr) if rcon_ptr else None, C.c_void_p(rk_ptr)))
+
+    def client_set_secret_keys(self, lwe_sk, glwe_sk):
+        a = np.ascontiguousarray(lwe_sk, dtype=np.uint64)
+        b = np.ascontiguousarray(glwe_sk, dtype=np.uint64)
+        self._ck(self.lib.tfa_client_set_secret_keys(self.h, _p(a), _p(b)))
 
     # -- keys ------------------------------------------------------------------------------------
     def load_keys(self, bsk, ksk, pfpksk):

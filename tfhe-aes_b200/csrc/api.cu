@@ -548,6 +548,12 @@ extern "C" int tfa_bootstrap(tfa_ctx *ctx, const uint64_t *in, int count, const 
     SYNC();
     return TFA_OK;
 }
+extern "C" int tfa_bootstrap_dev(tfa_ctx *ctx, const uint64_t *in, int count, const uint64_t *lut, uint64_t pre_add_body,
+                                 uint64_t post_add_body, uint64_t *out) {
+    Guard g(ctx);
+    RC(require_keys(ctx));
+    return dev_pbs(ctx, in, count, lut, 1, pre_add_body, post_add_body, out);
+}
 extern "C" int tfa_extract_bits(tfa_ctx *ctx, const uint64_t *in, int count, int delta_log, int nbits, uint64_t *out) {
     Guard g(ctx);
     RC(require_keys(ctx));

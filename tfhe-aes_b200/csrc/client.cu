@@ -231,3 +231,15 @@ extern "C" int tfa_client_secret_keys(tfa_ctx *ctx, uint64_t *lwe_sk, uint64_t *
     memcpy(glwe_sk, ctx->h_glwe_sk.data(), ctx->h_glwe_sk.size() * 8);
     return TFA_OK;
 }
+extern "C" int tfa_client_set_secret_keys(tfa_ctx *ctx, const uint64_t *lwe_sk, const uint64_t *glwe_sk) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    ctx->h_lwe_sk.assign(lwe_sk, lwe_sk + ctx->n);
+    ctx->h_glwe_sk.assign(glwe_sk, glwe_sk + ctx->big);
+    if (!ctx->d_lwe_sk) CU(cudaMalloc(&ctx->d_lwe_sk, (size_t)ctx->n * 8));
+    if (!ctx->d_glwe_sk) CU(cudaMalloc(&ctx->d_glwe_sk, (size_t)ctx->big * 8));
+    CU(cudaMemcpyAsync(ctx->d_lwe_sk, lwe_sk, (size_t)ctx->n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_glwe_sk, glwe_sk, (size_t)ctx->big * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TFA_OK;
+}

@@ -77,6 +77,7 @@ extern "C" int tfa_ctx_create(const tfa_params *p, int device, void *stream, tfa
     ctx->big = ctx->k * ctx->N; ctx->lw = ctx->big + 1; ctx->gsz = (ctx->k + 1) * ctx->N;
     ctx->device = device;
     ctx->launches = 0;
+    ctx->profiling = false;
     ctx->own_stream = (stream == nullptr);
     ctx->stream = (cudaStream_t)stream;
     ctx->bsk_f = nullptr; ctx->ksk = nullptr; ctx->pfpksk = nullptr; ctx->ksk_colsum = nullptr; ctx->pfpksk_colsum = nullptr;
@@ -184,6 +185,7 @@ static int pick_G(int K, int count) {
 }
 
 int dev_fourier(tfa_ctx *ctx, const u64 *polys, long npoly, double2 *out) {
+    StageTimer t(ctx, ST_FOURIER);
     ConvertArgs a{polys, out, ctx->tw, npoly, ctx->k};
     CU(launch_fourier_convert(a, ctx->stream));
     ctx->launches++;
@@ -204,7 +206,11 @@ static int rows_per_split(int rows, int base_ctas) {
 int dev_keyswitch(tfa_ctx *ctx, const u64 *in, int count, u64 *out) {
     const int rows = ctx->big * ctx->p.ks_level, np = ctx->n + 1;
     WS(digits, uint16_t, (size_t)count * rows);
-    CU(launch_decompose(in, ctx->lw, ctx->big, count, ctx->p.ks_base_log, ctx->p.ks_level, digits, ctx->stream));
+    {
+        StageTimer t(ctx, ST_KS_DECOMP);
+        CU(launch_decompose(in, ctx->lw, ctx->big, count, ctx->p.ks_base_log, ctx->p.ks_level, digits, ctx->stream));
+    }
+    StageTimer t(ctx, ST_KS_GEMV);
     CU(launch_gemv_init(out, np, np, count, ctx->ksk_colsum, 1ull << (ctx->p.ks_base_log - 1), in, ctx->lw, ctx->big, ctx->n, ctx->stream));
     GemvArgs g{};
     g.digits = digits; g.key = ctx->ksk; g.out = out; g.key_stride = 0; g.key_row_stride = ctx->ks_cols_pad;
@@ -219,7 +225,11 @@ int dev_keyswitch(tfa_ctx *ctx, const u64 *in, int count, u64 *out) {
 int dev_pfks(tfa_ctx *ctx, const u64 *in, int count, u64 *out, int out_stride) {
     const int rows = (ctx->big + 1) * ctx->p.pfks_level, kp1 = ctx->k + 1;
     WS(digits, uint16_t, (size_t)count * rows);
-    CU(launch_decompose(in, ctx->lw, ctx->big + 1, count, ctx->p.pfks_base_log, ctx->p.pfks_level, digits, ctx->stream));
+    {
+        StageTimer t(ctx, ST_PFKS_DECOMP);
+        CU(launch_decompose(in, ctx->lw, ctx->big + 1, count, ctx->p.pfks_base_log, ctx->p.pfks_level, digits, ctx->stream));
+    }
+    StageTimer t(ctx, ST_PFKS_GEMV);
     CU(launch_gemv_init(out, out_stride, kp1 * ctx->gsz, count, ctx->pfpksk_colsum, 1ull << (ctx->p.pfks_base_log - 1), nullptr, 0, 0, 0, ctx->stream));
     GemvArgs g{};
     g.digits = digits; g.key = ctx->pfpksk; g.out = out; g.key_stride = (size_t)rows * ctx->gsz; g.key_row_stride = ctx->gsz;
@@ -232,6 +242,7 @@ int dev_pfks(tfa_ctx *ctx, const u64 *in, int count, u64 *out, int out_stride) {
 
 // SURVEY §9.4(3)
 int dev_pbs(tfa_ctx *ctx, const u64 *in, int count, const u64 *lut, u64 in_scale, u64 pre_add, u64 post_add, u64 *out) {
+    StageTimer t(ctx, ST_PBS);
     PbsArgs a{};
     a.lwe_in = in; a.bsk = ctx->bsk_f; a.tw = ctx->tw; a.lut = lut; a.out = out;
     a.in_scale = in_scale; a.pre_add_body = pre_add; a.post_add = post_add; a.lwe_dim = ctx->n; a.count = count;
@@ -302,6 +313,7 @@ int dev_vertical_packing(tfa_ctx *ctx, const double2 *ggsw_f, int njobs, int nbi
         u64 *src = bufa, *dst = bufb;
         int cnt = nleaf;
         for (int layer = 0; layer < tree; layer++, cnt >>= 1) {
+            StageTimer tm(ctx, ST_TREE);
             TreeArgs t{};
             t.ggsw_f = ggsw_f; t.tw = ctx->tw; t.in = src; t.out = dst; t.nbits = nbits; t.bit_index = nbits - tree + layer;
             t.npairs = nouts * cnt / 2; t.njobs = njobs;
@@ -312,6 +324,7 @@ int dev_vertical_packing(tfa_ctx *ctx, const double2 *ggsw_f, int njobs, int nbi
         }
         glwe_init = src;
     }
+    StageTimer tm(ctx, ST_VP);
     VpArgs v{};
     v.ggsw_f = ggsw_f; v.tw = ctx->tw; v.lut = lut; v.glwe_init = glwe_init; v.out = out;
     v.lut_job_stride = lut_job_stride; v.lut_out_stride = lut_out_stride;
@@ -362,10 +375,77 @@ int dev_many_wopbs(tfa_ctx *ctx, const u64 *ct_in, int nct, int nblocks, const u
 }
 
 int dev_lwe_sum(tfa_ctx *ctx, const std::vector<SumEntry> &entries, int unit_words) {
+    StageTimer t(ctx, ST_LINEAR);
     WS(d, SumEntry, entries.size());
     CU(cudaMemcpyAsync(d, entries.data(), entries.size() * sizeof(SumEntry), cudaMemcpyHostToDevice, ctx->stream));
     // the host vector may die right after this call: make the copy complete (pageable source => staged synchronously)
     CU(launch_lwe_sum(d, (int)entries.size(), unit_words, ctx->stream));
     ctx->launches++;
+    return TFA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-stage GPU timing
+// ------------------------------------------------------------------------------------------------
+extern "C" int tfa_ctx_profile(tfa_ctx *ctx, int enable) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    ctx->prof.clear();
+    ctx->profiling = enable != 0;
+    return TFA_OK;
+}
+extern "C" int tfa_ctx_profile_report(tfa_ctx *ctx, double *ms_per_stage /* [10] */, int *launch_groups /* [10] */) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ST_COUNT; i++) { ms_per_stage[i] = 0; launch_groups[i] = 0; }
+    for (auto &r : ctx->prof) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_per_stage[r.stage] += ms; launch_groups[r.stage]++;
+    }
+    return TFA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// measured FP64 pipe peak (SURVEY §8d asks for a DFMA microbenchmark: B200's FP64 peak is not in
+// MEASURED_PEAKS.json).  16 independent FMA chains per thread, 2 CTAs of 512 threads per SM.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) dfma_peak_kernel(double *out, int iters, double a, double b) {
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] = fma(x[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += x[i];
+    if (s == 123.456) out[0] = s;
+}
+extern "C" int tfa_measure_fp64_peak(tfa_ctx *ctx, double *tflops) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    double *d = nullptr;
+    CU(cudaMalloc(&d, 8));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const int iters = 20000, grid = sms * 2;
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(e0, ctx->stream));
+        dfma_peak_kernel<<<grid, 512, 0, ctx->stream>>>(d, iters, 1.0000001, 1e-9);
+        CU(cudaEventRecord(e1, ctx->stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 16 * iters * 512.0 * grid;
+        if (rep > 0 && fl / (ms * 1e-3) * 1e-12 > best) best = fl / (ms * 1e-3) * 1e-12;
+    }
+    ctx->launches += 5;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best;
     return TFA_OK;
 }

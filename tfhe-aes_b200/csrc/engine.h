@@ -36,6 +36,11 @@ struct tfa_ctx {
     // cached device LUT sets (sbox module): [0]=S [1]={S,2S,3S} [2]=invS [3]={9,11,13,14}x [4]=identity
     u64 *lut_cache[5];
 
+    // optional per-stage GPU timing (tfa_ctx_profile): events around every launch group
+    bool profiling;
+    struct ProfRec { int stage; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+
     // bump workspace
     char *ws;
     size_t ws_cap, ws_off;
@@ -62,6 +67,19 @@ struct tfa_ctx {
         int r__ = (call);         \
         if (r__ != TFA_OK) return r__; \
     } while (0)
+
+enum { ST_KS_DECOMP = 0, ST_KS_GEMV, ST_PBS, ST_PFKS_DECOMP, ST_PFKS_GEMV, ST_FOURIER, ST_VP, ST_TREE, ST_LINEAR, ST_MISC, ST_COUNT };
+struct StageTimer {  // RAII: records two events on the context stream when profiling is on
+    tfa_ctx *ctx; int idx;
+    StageTimer(tfa_ctx *c, int stage) : ctx(c), idx(-1) {
+        if (!c->profiling) return;
+        tfa_ctx::ProfRec r; r.stage = stage;
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, c->stream);
+        idx = (int)c->prof.size(); c->prof.push_back(r);
+    }
+    ~StageTimer() { if (idx >= 0) cudaEventRecord(ctx->prof[idx].b, ctx->stream); }
+};
 
 // workspace helpers
 int ws_reserve(tfa_ctx *ctx, size_t bytes);      // make sure `bytes` of scratch are available, reset the bump pointer
