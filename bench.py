@@ -178,7 +178,9 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     pkg = load_pkg()
-    stream = torch.cuda.current_stream()
+    # every kernel of the library runs on this (non-default) stream; the timing events are recorded on it too
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     eng = pkg.Engine(pkg.param_opt(), device=local, stream=stream.cuda_stream)
     lw, B = eng.lw, args.blocks_per_gpu
     state_words = 16 * 8 * lw

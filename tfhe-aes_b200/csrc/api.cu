@@ -615,22 +615,11 @@ extern "C" int tfa_vertical_packing(tfa_ctx *ctx, const uint64_t *lut, int nouts
 }
 extern "C" int tfa_fourier_forward(tfa_ctx *ctx, const uint64_t *polys, int count, double *out) {
     Guard g(ctx);
-    // the kernel writes [row][p][col] with col = poly % (k+1); run it with groups of k+1 polynomials and undo the interleave
-    const int kp1 = ctx->k + 1;
-    const int padded = (count + kp1 - 1) / kp1 * kp1;
-    RC(ws_reserve(ctx, (size_t)padded * ctx->N * 8 * 2 + (1 << 20)));
-    WSB(d_in, u64, (size_t)padded * ctx->N); WSB(d_out, double2, (size_t)padded * 256);
-    CU(cudaMemsetAsync(d_in, 0, (size_t)padded * ctx->N * 8, ctx->stream));
+    RC(ws_reserve(ctx, (size_t)count * ctx->N * 8 * 2 + (1 << 20)));
+    WSB(d_in, u64, (size_t)count * ctx->N); WSB(d_out, double2, (size_t)count * 256);
     H2D(d_in, polys, (size_t)count * ctx->N);
-    RC(dev_fourier(ctx, d_in, padded, d_out));
-    std::vector<double2> h((size_t)padded * 256);
-    CU(cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    RC(dev_fourier(ctx, d_in, count, d_out));
+    CU(cudaMemcpyAsync(out, d_out, (size_t)count * 256 * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
     SYNC();
-    for (int q = 0; q < count; q++)
-        for (int p = 0; p < 256; p++) {
-            const double2 v = h[((size_t)(q / kp1) * 256 + p) * kp1 + (q % kp1)];
-            out[((size_t)q * 256 + p) * 2] = v.x;
-            out[((size_t)q * 256 + p) * 2 + 1] = v.y;
-        }
     return TFA_OK;
 }

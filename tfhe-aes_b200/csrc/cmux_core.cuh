@@ -13,7 +13,8 @@
 //   FFT phases:  group g handles polynomial r = g % (K+1) of ciphertext ct = g / (K+1)
 //                (G*(K+1) <= 16 groups busy).  Lane n2 owns coefficients 16 n1 + n2 (+256).
 //   MAC phase:   thread p owns Fourier point p of all G ciphertexts and all K+1 output
-//                polynomials; the GGSW value for (level, row, p, *) is loaded once and used G times.
+//                polynomials; the GGSW value for (level, row, *, p) is loaded once and used G times.
+// Fourier GGSW layout: [level][row][col][p] complex, level 1 first, p = natural DFT index.
 // The phases below are separate __host__ __device__ functions so that emu.cu can run them on the CPU
 // thread by thread; the kernels call them with barriers in between.
 #pragma once
@@ -139,20 +140,20 @@ HD void phase_fwd3(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) {
     for (int k2 = 0; k2 < 16; k2++) sm.xb[gid][lane + 16 * k2] = rg.v[rev4(k2)];
 }
 // ---- multiply-accumulate of one level against the Fourier GGSW -------------------------------
-// ggsw_level points at [row r][point p][col c] complex of this level.
+// ggsw_level points at [row r][col c][point p] complex of this level.
 template <int K, int G>
 HD void phase_mac(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg, const cd *__restrict__ ggsw_level) {
     const int p = tid;
 #pragma unroll
     for (int r = 0; r <= K; r++) {
         cd w[K + 1];
-        const cd *g = ggsw_level + ((size_t)r * POLY_M + p) * (K + 1);
+        const cd *g = ggsw_level + (size_t)r * (K + 1) * POLY_M + p;
 #pragma unroll
         for (int c = 0; c <= K; c++) {
 #ifdef __CUDA_ARCH__
-            w[c] = __ldg(g + c);
+            w[c] = __ldg(g + c * POLY_M);
 #else
-            w[c] = g[c];
+            w[c] = g[c * POLY_M];
 #endif
         }
 #pragma unroll
@@ -161,6 +162,20 @@ HD void phase_mac(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg, const cd *__r
 #pragma unroll
             for (int c = 0; c <= K; c++) cmac(rg.facc[ct][c], x, w[c]);
         }
+    }
+}
+// one GGSW row (fixed level and row r) whose K+1 values for this thread's point are at w_ptr[c * 256]
+// (shared-memory ring slot filled by cp.async in the PBS kernel, or global memory in the emulation)
+template <int K, int G>
+HD void phase_mac_row(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg, int r, const cd *w_ptr) {
+    cd w[K + 1];
+#pragma unroll
+    for (int c = 0; c <= K; c++) w[c] = w_ptr[c * POLY_M];
+#pragma unroll
+    for (int ct = 0; ct < G; ct++) {
+        const cd x = sm.xb[ct * (K + 1) + r][tid];
+#pragma unroll
+        for (int c = 0; c <= K; c++) cmac(rg.facc[ct][c], x, w[c]);
     }
 }
 // ---- inverse transform of the K+1 accumulators of every ciphertext and update of acc ----------

@@ -48,7 +48,7 @@ static void emu_forward(const uint64_t *poly, cd *out) {
     for (int lane = 0; lane < 16; lane++)
         for (int k2 = 0; k2 < 16; k2++) out[lane + 16 * k2] = v[lane][rev4(k2)];
 }
-// standard GGSW [level][row][col][N] -> kernel Fourier layout [level][row][p][col]
+// standard GGSW [level][row][col][N] -> kernel Fourier layout [level][row][col][p]
 template <int K>
 static void emu_convert_ggsw(const uint64_t *ggsw_std, int levels, cd *out) {
     cd tmp[POLY_M];
@@ -56,7 +56,7 @@ static void emu_convert_ggsw(const uint64_t *ggsw_std, int levels, cd *out) {
         for (int r = 0; r <= K; r++)
             for (int c = 0; c <= K; c++) {
                 emu_forward(ggsw_std + (((size_t)l * (K + 1) + r) * (K + 1) + c) * POLY_N, tmp);
-                for (int p = 0; p < POLY_M; p++) out[(((size_t)l * (K + 1) + r) * POLY_M + p) * (K + 1) + c] = tmp[p];
+                for (int p = 0; p < POLY_M; p++) out[(((size_t)l * (K + 1) + r) * (K + 1) + c) * POLY_M + p] = tmp[p];
             }
 }
 

@@ -20,7 +20,7 @@ struct tfa_ctx {
     u64 launches;
 
     // prepared keys (device)
-    double2 *bsk_f;        // [n][pbs_level][k+1][256][k+1]
+    double2 *bsk_f;        // [n][pbs_level][k+1][k+1][256]
     u64 *ksk;              // [big*ks_level][ks_cols_pad]
     u64 *pfpksk;           // [k+1][(big+1)*pfks_level][gsz]
     u64 *ksk_colsum;       // [ks_cols_pad]

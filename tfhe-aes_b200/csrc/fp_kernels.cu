@@ -59,16 +59,58 @@ __device__ __forceinline__ void sample_extract(int tid, const CmuxSmem<K, G> &sm
 
 // ------------------------------------------------------------------------------------------------
 // PBS: out[ct] = SampleExtract( BlindRotate(lut * X^-b~, a~, BSK) ) + post_add on the body
+//
+// Bootstrap-key streaming: the Fourier BSK slice of one CMux step is 25 rows x 20 KB (K=4).  Every
+// thread owns Fourier point p = tid and needs, per row, the K+1 complex values [row][0..K][p]
+// (each cp.async instruction of a warp moves 512 contiguous bytes).
+// Those are prefetched with cp.async.cg (L2 -> shared memory, no register staging) into a ring of
+// BSK_RING row-slots, thread-private (each thread only reads what it copied itself, so
+// cp.async.wait_group is the only synchronisation), BSK_RING rows ahead of the multiply-accumulate
+// that consumes them — across level and iteration boundaries, so the L2 latency is hidden behind the
+// FFT phases.  All CTAs walk the key in the same order, so the slice is an L2 hit for all but the first.
 // ------------------------------------------------------------------------------------------------
+#define BSK_RING 4
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 template <int K, int G, int BASE_LOG, int LEVELS>
 __global__ void __launch_bounds__(CMUX_THREADS, 1) pbs_kernel(PbsArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CmuxSmem<K, G> &sm = smem_view<K, G>(smem_raw);
-    uint16_t *ahat = reinterpret_cast<uint16_t *>(smem_raw + sizeof(CmuxSmem<K, G>));
+    cd *ring = reinterpret_cast<cd *>(smem_raw + sizeof(CmuxSmem<K, G>));            // [BSK_RING][256][K+1]
+    uint16_t *ahat = reinterpret_cast<uint16_t *>(ring + BSK_RING * POLY_M * (K + 1));
     CmuxRegs<K, G> rg;
     const int tid = threadIdx.x;
     const int n = a.lwe_dim, np = a.lwe_dim + 1;
     const int ct0 = blockIdx.x * G;
+    constexpr int ROWS = LEVELS * (K + 1);               // GGSW rows per CMux step, consumed level LEVELS first
+    constexpr size_t ROW_ELEMS = (size_t)POLY_M * (K + 1);
+    // prefetch head: row `pf` of the whole key walk (n * ROWS rows); memory order inside a step is
+    // level 1 first, so consumption index q (0..ROWS-1) maps to memory row (LEVELS-1 - q/(K+1))*(K+1) + q%(K+1)
+    const long total_rows = (long)n * ROWS;
+    long pf = 0;
+    int pf_q = 0;                                        // pf % ROWS
+    const cd *pf_step = a.bsk;                           // base of the CMux step the head is in
+    auto issue = [&]() {
+        if (pf < total_rows) {
+            const int mem_row = (LEVELS - 1 - pf_q / (K + 1)) * (K + 1) + pf_q % (K + 1);
+            const cd *src = pf_step + (size_t)mem_row * ROW_ELEMS + tid;
+            cd *dst = ring + (size_t)(pf % BSK_RING) * ROW_ELEMS + tid;
+#pragma unroll
+            for (int c = 0; c <= K; c++) cp_async16(dst + c * POLY_M, src + c * POLY_M);
+            pf++;
+            if (++pf_q == ROWS) { pf_q = 0; pf_step += (size_t)ROWS * ROW_ELEMS; }
+        }
+        cp_async_commit();                               // always commit: keeps the group count uniform
+    };
+#pragma unroll
+    for (int s = 0; s < BSK_RING; s++) issue();
+
     load_twiddles<K, G>(sm, a.tw, tid);
     // modulus switch to 2N: a~ = (a + 2^53) >> 54
     for (int idx = tid; idx < G * np; idx += CMUX_THREADS) {
@@ -87,18 +129,43 @@ __global__ void __launch_bounds__(CMUX_THREADS, 1) pbs_kernel(PbsArgs a) {
             sm.acc[g][r][j] = (r == K) ? rotated_coef(a.lut, j, rot) : 0;
         }
     }
+    if (tid < G) sm.rot[tid] = ahat[tid * np];
     __syncthreads();
-    const size_t ggsw_stride = (size_t)LEVELS * (K + 1) * POLY_M * (K + 1);
+    long row = 0;                                        // consumption index of the key walk
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
-        if (tid < G) sm.rot[tid] = ahat[tid * np + i];
-        __syncthreads();
-        bool any = false;
+        // a step whose rotations are all zero adds exactly zero (ct1 == 0): it is executed like any
+        // other so that the key walk stays in lock-step with the prefetch ring
+        phase_load_decompose<K, G, BASE_LOG, LEVELS, DIFF_ROTATE>(tid, sm, rg, nullptr);
+#pragma unroll 1
+        for (int lev = LEVELS; lev >= 1; lev--) {
+            if (lev != LEVELS) phase_next_digits<K, G, BASE_LOG>(tid, rg);
+            phase_fwd1<K, G>(tid, sm, rg);
+            __syncwarp();
+            phase_fwd2<K, G>(tid, sm, rg);
+            __syncwarp();
+            phase_fwd3<K, G>(tid, sm, rg);
+            __syncthreads();
 #pragma unroll
-        for (int g = 0; g < G; g++) any |= (sm.rot[g] != 0);
-        if (!any) { __syncthreads(); continue; }  // every ct1 would be identically zero
-        cmux_step<K, G, BASE_LOG, LEVELS, DIFF_ROTATE>(tid, sm, rg, a.bsk + (size_t)i * ggsw_stride, nullptr);
+            for (int r = 0; r <= K; r++) {
+                cp_async_wait<BSK_RING - 1>();
+                phase_mac_row<K, G>(tid, sm, rg, r, ring + (size_t)(row % BSK_RING) * ROW_ELEMS + tid);
+                row++;
+                issue();
+            }
+            __syncthreads();
+        }
+        phase_inv0<K, G>(tid, sm, rg);
+        __syncthreads();
+        phase_inv1<K, G>(tid, sm, rg);
+        __syncwarp();
+        phase_inv2<K, G>(tid, sm, rg);
+        __syncwarp();
+        phase_inv3<K, G>(tid, sm, rg);
+        if (tid < G && i + 1 < n) sm.rot[tid] = ahat[tid * np + i + 1];
+        __syncthreads();
     }
+    cp_async_wait<0>();
     for (int g = 0; g < G; g++)
         if (ct0 + g < a.count) sample_extract<K, G>(tid, sm, g, a.out + (size_t)(ct0 + g) * (K * POLY_N + 1), a.post_add);
 }
@@ -173,7 +240,7 @@ __global__ void __launch_bounds__(CMUX_THREADS, 1) cmux_tree_kernel(TreeArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// standard-domain GGSW list [g][level][row][col][N] (u64) -> Fourier layout [g][level][row][p][col]
+// standard-domain GGSW list [g][level][row][col][N] (u64) -> Fourier layout [g][level][row][col][p]
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CMUX_THREADS, 2) fourier_convert_kernel(ConvertArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -186,7 +253,6 @@ __global__ void __launch_bounds__(CMUX_THREADS, 2) fourier_convert_kernel(Conver
     const bool active = q < a.npoly;
     cd *xb = xb_all + gid * XB_ELEMS;
     cd v[16];
-    const int kp1 = a.glwe_dim + 1;
     if (active) {
         load_torus_poly(v, lane, a.in + (size_t)q * POLY_N);
         fft256_fwd_pass1(v, lane, tw, xb);
@@ -194,10 +260,9 @@ __global__ void __launch_bounds__(CMUX_THREADS, 2) fourier_convert_kernel(Conver
     __syncwarp();
     if (active) {
         fft256_fwd_pass2(v, lane, xb);
-        const long col = q % kp1, row_idx = q / kp1;  // row_idx = ((g*L + lev)*(K+1) + row)
-        cd *dst = a.out + ((size_t)row_idx * POLY_M) * kp1 + col;
+        cd *dst = a.out + (size_t)q * POLY_M;  // natural order: [g][level][row][col][p]
 #pragma unroll
-        for (int k2 = 0; k2 < 16; k2++) dst[(size_t)(lane + 16 * k2) * kp1] = v[rev4(k2)];
+        for (int k2 = 0; k2 < 16; k2++) dst[lane + 16 * k2] = v[rev4(k2)];
     }
 }
 
@@ -211,7 +276,8 @@ static cudaError_t set_smem(F f, size_t bytes) {
 
 #define LAUNCH_PBS(k, g, bl, lv)                                                               \
     if (K == k && G == g && base_log == bl && levels == lv) {                                  \
-        size_t smem = sizeof(CmuxSmem<k, g>) + (size_t)g * (a.lwe_dim + 1) * sizeof(uint16_t); \
+        size_t smem = sizeof(CmuxSmem<k, g>) + (size_t)BSK_RING * POLY_M * (k + 1) * sizeof(cd) + \
+                      (size_t)g * (a.lwe_dim + 1) * sizeof(uint16_t);                            \
         cudaError_t e = set_smem(pbs_kernel<k, g, bl, lv>, smem);                              \
         if (e != cudaSuccess) return e;                                                        \
         pbs_kernel<k, g, bl, lv><<<(a.count + g - 1) / g, CMUX_THREADS, smem, s>>>(a);         \

@@ -5,7 +5,7 @@
 
 struct PbsArgs {
     const uint64_t *lwe_in;   // [count][lwe_dim+1]
-    const double2 *bsk;       // Fourier BSK [lwe_dim][level][row][p][col]
+    const double2 *bsk;       // Fourier BSK [lwe_dim][level][row][col][p]
     const double2 *tw;        // 512 twiddles (make_twiddle_tables)
     const uint64_t *lut;      // [N] body of the trivial accumulator
     uint64_t *out;            // [count][k*N+1]
@@ -16,7 +16,7 @@ struct PbsArgs {
     int count;
 };
 struct VpArgs {
-    const double2 *ggsw_f;    // [njobs][nbits][level][row][p][col], bit 0 = LSB
+    const double2 *ggsw_f;    // [njobs][nbits][level][row][col][p], bit 0 = LSB
     const double2 *tw;
     const uint64_t *lut;      // [.. job*lut_job_stride + out*lut_out_stride + j ..] LUT polynomial per output (if glwe_init == 0)
     const uint64_t *glwe_init;// or [njobs][nouts][(k+1)N] start accumulators (root of the CMux tree)
@@ -40,7 +40,7 @@ struct TreeArgs {
 };
 struct ConvertArgs {
     const uint64_t *in;       // [npoly][N], polys ordered [g][level][row][col]
-    double2 *out;             // [g][level][row][p][col]
+    double2 *out;             // [g][level][row][col][p]
     const double2 *tw;
     long npoly;
     int glwe_dim;
