@@ -607,7 +607,7 @@ extern "C" int tfa_vertical_packing(tfa_ctx *ctx, const uint64_t *lut, int nouts
     WSB(d_lut, u64, lw_); WSB(d_out, u64, ow); WSB(d_g, u64, gw * nggsw); WSB(d_gf, double2, gw * nggsw / 2);
     H2D(d_lut, lut, lw_);
     for (int i = 0; i < nggsw; i++) H2D(d_g + (size_t)i * gw, ggsw_std + (size_t)(nggsw - 1 - i) * gw, gw);  // to LSB-first
-    RC(dev_fourier(ctx, d_g, (long)nggsw * ctx->p.cbs_level * (ctx->k + 1) * (ctx->k + 1), d_gf));
+    RC(dev_fourier(ctx, d_g, (long)nggsw * ctx->p.cbs_level * (ctx->k + 1) * (ctx->k + 1), ctx->p.cbs_level, d_gf));
     RC(dev_vertical_packing(ctx, d_gf, 1, nggsw, d_lut, 0, (size_t)npoly * ctx->N, nouts, npoly * ctx->N, d_out));
     D2H(out, d_out, ow);
     SYNC();
@@ -618,7 +618,7 @@ extern "C" int tfa_fourier_forward(tfa_ctx *ctx, const uint64_t *polys, int coun
     RC(ws_reserve(ctx, (size_t)count * ctx->N * 8 * 2 + (1 << 20)));
     WSB(d_in, u64, (size_t)count * ctx->N); WSB(d_out, double2, (size_t)count * 256);
     H2D(d_in, polys, (size_t)count * ctx->N);
-    RC(dev_fourier(ctx, d_in, count, d_out));
+    RC(dev_fourier(ctx, d_in, count, 1, d_out));
     CU(cudaMemcpyAsync(out, d_out, (size_t)count * 256 * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
     SYNC();
     return TFA_OK;

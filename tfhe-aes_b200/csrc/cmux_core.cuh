@@ -14,7 +14,8 @@
 //                (G*(K+1) <= 16 groups busy).  Lane n2 owns coefficients 16 n1 + n2 (+256).
 //   MAC phase:   thread p owns Fourier point p of all G ciphertexts and all K+1 output
 //                polynomials; the GGSW value for (level, row, *, p) is loaded once and used G times.
-// Fourier GGSW layout: [level][row][col][p] complex, level 1 first, p = natural DFT index.
+// Fourier GGSW layout: [level slot][row][col][p] complex, slot 0 = level LEVELS (the order in which the
+// decomposition produces the digits), p = natural DFT index.
 // The phases below are separate __host__ __device__ functions so that emu.cu can run them on the CPU
 // thread by thread; the kernels call them with barriers in between.
 #pragma once
@@ -90,14 +91,21 @@ HD void phase_load_decompose(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg, co
     if (gid >= G * (K + 1)) return;
     const int ct = gid / (K + 1), r = gid % (K + 1);
     const uint64_t *poly = sm.acc[ct][r];
-    const int rot = sm.rot[ct];
+    const int s0 = (lane - sm.rot[ct]) & (2 * POLY_N - 1);
 #pragma unroll
     for (int n1 = 0; n1 < 16; n1++) {
         const int j = 16 * n1 + lane;
         uint64_t a0, a1;
         if (MODE == DIFF_ROTATE) {
-            a0 = rotated_coef(poly, j, rot) - poly[j];
-            a1 = rotated_coef(poly, j + POLY_M, rot) - poly[j + POLY_M];
+            // (acc * X^rot)[j] and [j + 256]: source index s = j - rot mod 2N, sign flips when s >= N;
+            // adding 256 to j toggles bit 8 of s and carries into the sign bit
+            const int s = (s0 + 16 * n1) & (2 * POLY_N - 1);
+            const int i0 = s & (POLY_N - 1);
+            const uint64_t x0 = poly[i0], x1 = poly[i0 ^ POLY_M];
+            const uint64_t m0 = (uint64_t)0 - (uint64_t)((s >> 9) & 1);
+            const uint64_t m1 = (uint64_t)0 - (uint64_t)(((s >> 9) ^ (s >> 8)) & 1);
+            a0 = ((x0 ^ m0) - m0) - poly[j];
+            a1 = ((x1 ^ m1) - m1) - poly[j + POLY_M];
         } else {
             const uint64_t *e = ext[ct] + (size_t)r * POLY_N;
             a0 = e[j] - poly[j];
@@ -177,6 +185,23 @@ HD void phase_mac_row(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg, int r, co
 #pragma unroll
         for (int c = 0; c <= K; c++) cmac(rg.facc[ct][c], x, w[c]);
     }
+}
+// software-pipelined form: operands of the NEXT row are fetched while the current row is computed
+template <int K, int G>
+struct MacOperands { cd w[K + 1]; cd x[G]; };
+template <int K, int G>
+HD void mac_fetch(int tid, const CmuxSmem<K, G> &sm, int r, const cd *w_ptr, MacOperands<K, G> &o) {
+#pragma unroll
+    for (int c = 0; c <= K; c++) o.w[c] = w_ptr[c * POLY_M];
+#pragma unroll
+    for (int ct = 0; ct < G; ct++) o.x[ct] = sm.xb[ct * (K + 1) + r][tid];
+}
+template <int K, int G>
+HD void mac_compute(CmuxRegs<K, G> &rg, const MacOperands<K, G> &o) {
+#pragma unroll
+    for (int ct = 0; ct < G; ct++)
+#pragma unroll
+        for (int c = 0; c <= K; c++) cmac(rg.facc[ct][c], o.x[ct], o.w[c]);
 }
 // ---- inverse transform of the K+1 accumulators of every ciphertext and update of acc ----------
 template <int K, int G>

@@ -27,7 +27,7 @@ struct EmuCta {
             ALL((phase_fwd1<K, G>(tid, sm, rg[tid])));
             ALL((phase_fwd2<K, G>(tid, sm, rg[tid])));
             ALL((phase_fwd3<K, G>(tid, sm, rg[tid])));
-            ALL((phase_mac<K, G>(tid, sm, rg[tid], ggsw + (size_t)(lev - 1) * (K + 1) * POLY_M * (K + 1))));
+            ALL((phase_mac<K, G>(tid, sm, rg[tid], ggsw + (size_t)(LEVELS - lev) * (K + 1) * POLY_M * (K + 1))));
         }
         ALL((phase_inv0<K, G>(tid, sm, rg[tid])));
         ALL((phase_inv1<K, G>(tid, sm, rg[tid])));
@@ -56,7 +56,7 @@ static void emu_convert_ggsw(const uint64_t *ggsw_std, int levels, cd *out) {
         for (int r = 0; r <= K; r++)
             for (int c = 0; c <= K; c++) {
                 emu_forward(ggsw_std + (((size_t)l * (K + 1) + r) * (K + 1) + c) * POLY_N, tmp);
-                for (int p = 0; p < POLY_M; p++) out[(((size_t)l * (K + 1) + r) * (K + 1) + c) * POLY_M + p] = tmp[p];
+                for (int p = 0; p < POLY_M; p++) out[(((size_t)(levels - 1 - l) * (K + 1) + r) * (K + 1) + c) * POLY_M + p] = tmp[p];
             }
 }
 

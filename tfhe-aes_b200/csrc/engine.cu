@@ -148,7 +148,7 @@ extern "C" int tfa_ctx_keys_ready(tfa_ctx *ctx) {
 // ksk already in padded layout in ctx->ksk, pfpksk already in ctx->pfpksk
 int prepare_keys_from_device(tfa_ctx *ctx, const u64 *bsk_std_dev) {
     const long npoly = (long)ctx->n * ctx->p.pbs_level * (ctx->k + 1) * (ctx->k + 1);
-    RC(dev_fourier(ctx, bsk_std_dev, npoly, ctx->bsk_f));
+    RC(dev_fourier(ctx, bsk_std_dev, npoly, ctx->p.pbs_level, ctx->bsk_f));
     CU(launch_key_colsum(ctx->ksk, ctx->big * ctx->p.ks_level, ctx->ks_cols_pad, ctx->ks_cols_pad, 1, 0, ctx->ksk_colsum, ctx->stream));
     const int prow = (ctx->big + 1) * ctx->p.pfks_level;
     CU(launch_key_colsum(ctx->pfpksk, prow, ctx->gsz, ctx->gsz, ctx->k + 1, (size_t)prow * ctx->gsz, ctx->pfpksk_colsum, ctx->stream));
@@ -184,22 +184,22 @@ static int pick_G(int K, int count) {
     return count >= 16 ? 8 : (count >= 4 ? 4 : 1);
 }
 
-int dev_fourier(tfa_ctx *ctx, const u64 *polys, long npoly, double2 *out) {
+int dev_fourier(tfa_ctx *ctx, const u64 *polys, long npoly, int levels, double2 *out) {
     StageTimer t(ctx, ST_FOURIER);
-    ConvertArgs a{polys, out, ctx->tw, npoly, ctx->k};
+    ConvertArgs a{polys, out, ctx->tw, npoly, ctx->k, levels};
     CU(launch_fourier_convert(a, ctx->stream));
     ctx->launches++;
     return TFA_OK;
 }
 
 static int rows_per_split(int rows, int base_ctas) {
-    // aim for >= ~2 waves of CTAs; splits in whole chunks of 512 rows
-    int want = (2 * 148 + base_ctas - 1) / base_ctas;
+    // aim for >= ~2 waves of CTAs (2 resident per SM); splits in whole chunks of 256 rows
+    int want = (4 * 148 + base_ctas - 1) / base_ctas;
     if (want < 1) want = 1;
-    int chunks = (rows + 511) / 512;
+    int chunks = (rows + 255) / 256;
     if (want > chunks) want = chunks;
     int per = (chunks + want - 1) / want;
-    return per * 512;
+    return per * 256;
 }
 
 // out = (0,..,0,b) - sum_i sum_l d_{i,l} KSK[i][l]
@@ -215,7 +215,7 @@ int dev_keyswitch(tfa_ctx *ctx, const u64 *in, int count, u64 *out) {
     GemvArgs g{};
     g.digits = digits; g.key = ctx->ksk; g.out = out; g.key_stride = 0; g.key_row_stride = ctx->ks_cols_pad;
     g.out_stride = np; g.rows = rows; g.ncols = np; g.nkeys = 1; g.count = count;
-    g.rows_per_split = rows_per_split(rows, ((np + 511) / 512) * ((count + 7) / 8));
+    g.rows_per_split = rows_per_split(rows, ((np + 255) / 256) * ((count + 31) / 32));
     CU(launch_gemv(g, ctx->stream));
     ctx->launches += 3;
     return TFA_OK;
@@ -234,7 +234,7 @@ int dev_pfks(tfa_ctx *ctx, const u64 *in, int count, u64 *out, int out_stride) {
     GemvArgs g{};
     g.digits = digits; g.key = ctx->pfpksk; g.out = out; g.key_stride = (size_t)rows * ctx->gsz; g.key_row_stride = ctx->gsz;
     g.out_stride = out_stride; g.rows = rows; g.ncols = ctx->gsz; g.nkeys = kp1; g.count = count;
-    g.rows_per_split = rows_per_split(rows, ((ctx->gsz + 511) / 512) * ((count + 7) / 8) * kp1);
+    g.rows_per_split = rows_per_split(rows, ((ctx->gsz + 255) / 256) * ((count + 31) / 32) * kp1);
     CU(launch_gemv(g, ctx->stream));
     ctx->launches += 3;
     return TFA_OK;
@@ -369,7 +369,7 @@ int dev_many_wopbs(tfa_ctx *ctx, const u64 *ct_in, int nct, int nblocks, const u
     WS(ggsw_std, u64, (size_t)nb * ggsw_words);
     WS(ggsw_f, double2, (size_t)nb * ggsw_words / 2);
     RC(dev_circuit_bootstrap(ctx, bits, nb, ggsw_std));
-    RC(dev_fourier(ctx, ggsw_std, (long)nb * ctx->p.cbs_level * (ctx->k + 1) * (ctx->k + 1), ggsw_f));
+    RC(dev_fourier(ctx, ggsw_std, (long)nb * ctx->p.cbs_level * (ctx->k + 1) * (ctx->k + 1), ctx->p.cbs_level, ggsw_f));
     // (3) one vertical packing per LUT output (many_wopbs.rs:267-279)
     return dev_vertical_packing(ctx, ggsw_f, nct, nbits, lut, lut_job_stride, lut_out_stride, nouts, lut_size, out);
 }

@@ -91,7 +91,7 @@ static inline T *ws_get(tfa_ctx *ctx, size_t count) { return reinterpret_cast<T 
 int dev_keyswitch(tfa_ctx *ctx, const u64 *in, int count, u64 *out);
 int dev_pbs(tfa_ctx *ctx, const u64 *in, int count, const u64 *lut, u64 in_scale, u64 pre_add, u64 post_add, u64 *out);
 int dev_pfks(tfa_ctx *ctx, const u64 *in, int count, u64 *out, int out_stride);
-int dev_fourier(tfa_ctx *ctx, const u64 *polys, long npoly, double2 *out);
+int dev_fourier(tfa_ctx *ctx, const u64 *polys, long npoly, int levels, double2 *out);
 int dev_extract_bits(tfa_ctx *ctx, const u64 *in, int count, int delta_log, int nbits, u64 *out /* [count][nbits][n+1], 0 = LSB */);
 int dev_circuit_bootstrap(tfa_ctx *ctx, const u64 *lwe_small, int count, u64 *ggsw_std);
 int dev_vertical_packing(tfa_ctx *ctx, const double2 *ggsw_f, int njobs, int nbits, const u64 *lut, size_t lut_job_stride,

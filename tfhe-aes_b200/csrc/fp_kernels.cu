@@ -34,7 +34,7 @@ __device__ __forceinline__ void cmux_step(int tid, CmuxSmem<K, G> &sm, CmuxRegs<
         __syncwarp();
         phase_fwd3<K, G>(tid, sm, rg);
         __syncthreads();
-        phase_mac<K, G>(tid, sm, rg, ggsw + (size_t)(lev - 1) * (K + 1) * POLY_M * (K + 1));
+        phase_mac<K, G>(tid, sm, rg, ggsw + (size_t)(LEVELS - lev) * (K + 1) * POLY_M * (K + 1));
         __syncthreads();
     }
     phase_inv0<K, G>(tid, sm, rg);
@@ -88,23 +88,25 @@ __global__ void __launch_bounds__(CMUX_THREADS, 1) pbs_kernel(PbsArgs a) {
     const int tid = threadIdx.x;
     const int n = a.lwe_dim, np = a.lwe_dim + 1;
     const int ct0 = blockIdx.x * G;
-    constexpr int ROWS = LEVELS * (K + 1);               // GGSW rows per CMux step, consumed level LEVELS first
+    constexpr int ROWS = LEVELS * (K + 1);               // GGSW rows per CMux step, stored in consumption order
     constexpr size_t ROW_ELEMS = (size_t)POLY_M * (K + 1);
-    // prefetch head: row `pf` of the whole key walk (n * ROWS rows); memory order inside a step is
-    // level 1 first, so consumption index q (0..ROWS-1) maps to memory row (LEVELS-1 - q/(K+1))*(K+1) + q%(K+1)
-    const long total_rows = (long)n * ROWS;
-    long pf = 0;
-    int pf_q = 0;                                        // pf % ROWS
-    const cd *pf_step = a.bsk;                           // base of the CMux step the head is in
+    constexpr unsigned ROW_BYTES = (unsigned)(ROW_ELEMS * sizeof(cd));
+    constexpr unsigned RING_BYTES = BSK_RING * ROW_BYTES;
+    // prefetch head: the key is walked linearly, one row (K+1 polynomials of 256 points) at a time
+    const cd *pf_src = a.bsk + tid;
+    long pf_left = (long)n * ROWS;
+    const unsigned ring_u32 = (unsigned)__cvta_generic_to_shared(ring) + tid * (unsigned)sizeof(cd);
+    unsigned pf_off = 0;
     auto issue = [&]() {
-        if (pf < total_rows) {
-            const int mem_row = (LEVELS - 1 - pf_q / (K + 1)) * (K + 1) + pf_q % (K + 1);
-            const cd *src = pf_step + (size_t)mem_row * ROW_ELEMS + tid;
-            cd *dst = ring + (size_t)(pf % BSK_RING) * ROW_ELEMS + tid;
+        if (pf_left > 0) {
 #pragma unroll
-            for (int c = 0; c <= K; c++) cp_async16(dst + c * POLY_M, src + c * POLY_M);
-            pf++;
-            if (++pf_q == ROWS) { pf_q = 0; pf_step += (size_t)ROWS * ROW_ELEMS; }
+            for (int c = 0; c <= K; c++)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(ring_u32 + pf_off + c * (POLY_M * (unsigned)sizeof(cd))),
+                             "l"(pf_src + c * POLY_M));
+            pf_src += ROW_ELEMS;
+            pf_left--;
+            pf_off += ROW_BYTES;
+            if (pf_off == RING_BYTES) pf_off = 0;
         }
         cp_async_commit();                               // always commit: keeps the group count uniform
     };
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(CMUX_THREADS, 1) pbs_kernel(PbsArgs a) {
     }
     if (tid < G) sm.rot[tid] = ahat[tid * np];
     __syncthreads();
-    long row = 0;                                        // consumption index of the key walk
+    unsigned rd_off = 0;                                 // ring offset of the next row to consume
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
         // a step whose rotations are all zero adds exactly zero (ct1 == 0): it is executed like any
@@ -149,8 +151,9 @@ __global__ void __launch_bounds__(CMUX_THREADS, 1) pbs_kernel(PbsArgs a) {
 #pragma unroll
             for (int r = 0; r <= K; r++) {
                 cp_async_wait<BSK_RING - 1>();
-                phase_mac_row<K, G>(tid, sm, rg, r, ring + (size_t)(row % BSK_RING) * ROW_ELEMS + tid);
-                row++;
+                phase_mac_row<K, G>(tid, sm, rg, r, reinterpret_cast<const cd *>(reinterpret_cast<const unsigned char *>(ring) + rd_off) + tid);
+                rd_off += ROW_BYTES;
+                if (rd_off == RING_BYTES) rd_off = 0;
                 issue();
             }
             __syncthreads();
@@ -260,7 +263,11 @@ __global__ void __launch_bounds__(CMUX_THREADS, 2) fourier_convert_kernel(Conver
     __syncwarp();
     if (active) {
         fft256_fwd_pass2(v, lane, xb);
-        cd *dst = a.out + (size_t)q * POLY_M;  // natural order: [g][level][row][col][p]
+        // [g][level][row][col] -> [g][level slot = levels-1-level][row][col][p]
+        const long per_level = (long)(a.glwe_dim + 1) * (a.glwe_dim + 1);
+        const long rc = q % per_level, gl = q / per_level;
+        const long lev = gl % a.levels, g = gl / a.levels;
+        cd *dst = a.out + (size_t)((g * a.levels + (a.levels - 1 - lev)) * per_level + rc) * POLY_M;
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) dst[lane + 16 * k2] = v[rev4(k2)];
     }

@@ -40,58 +40,73 @@ cudaError_t launch_decompose(const uint64_t *in, int in_stride, int nelem, int c
 }
 
 // ---- batched decomposed matrix-vector product -----------------------------------------------------
-// CTA tile: GEMV_TB ciphertexts x 512 columns (2 per thread, 128-bit key loads); rows streamed in
-// chunks of GEMV_RC with the digits of the tile staged in shared memory.
-#define GEMV_TB 8
-#define GEMV_RC 512
+// out[ct][key][col] -= sum_rows u[ct][row] * key[row][col]          (u64 wrapping, exact)
+// CTA tile: GEMV_TB ciphertexts x 256 columns (one per thread, coalesced 64-bit key loads), rows streamed
+// in chunks of GEMV_RC with the tile's digits staged in shared memory.  One key element feeds GEMV_TB
+// multiply-accumulates (IMAD.WIDE.U32 + IMAD each), so key traffic is 8 B per 32 MACs.
+// Grid order: the ciphertext tile is the FASTEST index, so CTAs that are resident together read the
+// same key chunk and all but the first hit L2; HBM sees each key byte about once per pass.
+// The u64 product sum is kept as two independent accumulators so that each multiply-accumulate costs one
+// IMAD.WIDE.U32 + one IMAD on the multiplier pipe (the 64-bit add of the low partial product goes to the
+// ALU pipe as IADD3 / IADD3.X):
+//   lo64 += u * k_lo          (u < 2^16, k_lo < 2^32, <= 2^13 rows: never overflows 64 bits)
+//   hi32 += u * k_hi          (mod 2^32)
+//   result = lo64 + (hi32 << 32)   (mod 2^64, exact)
+#define GEMV_TB 32
+#define GEMV_RC 256
 #define GEMV_THREADS 256
-__global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(GemvArgs a) {
+__global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(GemvArgs a) {
     __shared__ __align__(16) uint16_t sdig[GEMV_TB][GEMV_RC];
     const int tid = threadIdx.x;
-    const int col = blockIdx.x * (2 * GEMV_THREADS) + 2 * tid;
-    const int ntile_ct = (a.count + GEMV_TB - 1) / GEMV_TB;
-    const int keyi = blockIdx.y / ntile_ct;
-    const int ct0 = (blockIdx.y % ntile_ct) * GEMV_TB;
-    const int row_begin = blockIdx.z * a.rows_per_split;
+    const int ct0 = blockIdx.x * GEMV_TB;
+    const int col = blockIdx.y * GEMV_THREADS + tid;
+    const int nsplit = (a.rows + a.rows_per_split - 1) / a.rows_per_split;
+    const int keyi = blockIdx.z / nsplit;
+    const int row_begin = (blockIdx.z % nsplit) * a.rows_per_split;
     const int row_end = min(a.rows, row_begin + a.rows_per_split);
     const bool col_ok = col < a.ncols;
-    const uint64_t *key = a.key + (size_t)keyi * a.key_stride;
-    uint64_t acc0[GEMV_TB], acc1[GEMV_TB];
+    const uint64_t *key = a.key + (size_t)keyi * a.key_stride + (col_ok ? col : 0);
+    uint64_t acc_lo[GEMV_TB];
+    uint32_t acc_hi[GEMV_TB];
 #pragma unroll
-    for (int b = 0; b < GEMV_TB; b++) acc0[b] = acc1[b] = 0;
+    for (int b = 0; b < GEMV_TB; b++) { acc_lo[b] = 0; acc_hi[b] = 0; }
     for (int r0 = row_begin; r0 < row_end; r0 += GEMV_RC) {
         const int nr = min(GEMV_RC, row_end - r0);
         __syncthreads();
-        for (int i = tid; i < GEMV_TB * GEMV_RC; i += GEMV_THREADS) {
-            const int b = i / GEMV_RC, rr = i % GEMV_RC;
+        for (int i = tid; i < GEMV_TB * GEMV_RC / 4; i += GEMV_THREADS) {  // 4 digits (8 B) per access
+            const int b = i / (GEMV_RC / 4), rr = (i % (GEMV_RC / 4)) * 4;
             const int ct = ct0 + b;
-            sdig[b][rr] = (rr < nr && ct < a.count) ? a.digits[(size_t)ct * a.rows + r0 + rr] : (uint16_t)0;
-        }
-        __syncthreads();
-        if (col_ok) {
-            const uint64_t *kp = key + (size_t)r0 * a.key_row_stride + col;
-            int rr = 0;
-            for (; rr + 4 <= nr; rr += 4) {
-                ulonglong2 k0 = __ldg(reinterpret_cast<const ulonglong2 *>(kp + (size_t)(rr + 0) * a.key_row_stride));
-                ulonglong2 k1 = __ldg(reinterpret_cast<const ulonglong2 *>(kp + (size_t)(rr + 1) * a.key_row_stride));
-                ulonglong2 k2 = __ldg(reinterpret_cast<const ulonglong2 *>(kp + (size_t)(rr + 2) * a.key_row_stride));
-                ulonglong2 k3 = __ldg(reinterpret_cast<const ulonglong2 *>(kp + (size_t)(rr + 3) * a.key_row_stride));
-#pragma unroll
-                for (int b = 0; b < GEMV_TB; b++) {
-                    const uint2 dd = *reinterpret_cast<const uint2 *>(&sdig[b][rr]);
-                    const uint32_t u0 = dd.x & 0xFFFF, u1 = dd.x >> 16, u2 = dd.y & 0xFFFF, u3 = dd.y >> 16;
-                    acc0[b] += (uint64_t)u0 * k0.x + (uint64_t)u1 * k1.x + (uint64_t)u2 * k2.x + (uint64_t)u3 * k3.x;
-                    acc1[b] += (uint64_t)u0 * k0.y + (uint64_t)u1 * k1.y + (uint64_t)u2 * k2.y + (uint64_t)u3 * k3.y;
+            uint2 v = make_uint2(0, 0);
+            if (ct < a.count) {
+                const uint16_t *src = a.digits + (size_t)ct * a.rows + r0 + rr;
+                if (rr + 4 <= nr && ((reinterpret_cast<uintptr_t>(src) & 7) == 0)) v = *reinterpret_cast<const uint2 *>(src);
+                else {
+                    uint32_t d[4];
+                    for (int t = 0; t < 4; t++) d[t] = (rr + t < nr) ? src[t] : 0;
+                    v = make_uint2(d[0] | (d[1] << 16), d[2] | (d[3] << 16));
                 }
             }
-            for (; rr < nr; rr++) {
-                ulonglong2 k0 = __ldg(reinterpret_cast<const ulonglong2 *>(kp + (size_t)rr * a.key_row_stride));
+            *reinterpret_cast<uint2 *>(&sdig[b][rr]) = v;
+        }
+        __syncthreads();
+        const uint64_t *kp = key + (size_t)r0 * a.key_row_stride;
+        for (int rr = 0; rr < nr; rr += 4) {   // rows beyond nr carry zero digits; key reads are clamped
+            uint32_t klo[4], khi[4];
 #pragma unroll
-                for (int b = 0; b < GEMV_TB; b++) {
-                    const uint32_t u0 = sdig[b][rr];
-                    acc0[b] += (uint64_t)u0 * k0.x;
-                    acc1[b] += (uint64_t)u0 * k0.y;
-                }
+            for (int t = 0; t < 4; t++) {
+                const uint64_t k = __ldg(kp + (size_t)min(rr + t, nr - 1) * a.key_row_stride);
+                klo[t] = (uint32_t)k;
+                khi[t] = (uint32_t)(k >> 32);
+            }
+#pragma unroll
+            for (int b = 0; b < GEMV_TB; b++) {
+                const uint2 dd = *reinterpret_cast<const uint2 *>(&sdig[b][rr]);
+                const uint32_t u0 = dd.x & 0xFFFF, u1 = dd.x >> 16, u2 = dd.y & 0xFFFF, u3 = dd.y >> 16;
+                acc_lo[b] += (uint64_t)u0 * klo[0];
+                acc_lo[b] += (uint64_t)u1 * klo[1];
+                acc_lo[b] += (uint64_t)u2 * klo[2];
+                acc_lo[b] += (uint64_t)u3 * klo[3];
+                acc_hi[b] += u0 * khi[0] + u1 * khi[1] + u2 * khi[2] + u3 * khi[3];
             }
         }
     }
@@ -99,19 +114,17 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(GemvArgs a) {
 #pragma unroll
         for (int b = 0; b < GEMV_TB; b++) {
             const int ct = ct0 + b;
-            if (ct < a.count) {
-                unsigned long long *o = reinterpret_cast<unsigned long long *>(a.out + (size_t)ct * a.out_stride + (size_t)keyi * a.ncols + col);
-                atomicAdd(o, (unsigned long long)(0 - acc0[b]));
-                if (col + 1 < a.ncols) atomicAdd(o + 1, (unsigned long long)(0 - acc1[b]));
-            }
+            if (ct < a.count)
+                atomicAdd(reinterpret_cast<unsigned long long *>(a.out + (size_t)ct * a.out_stride + (size_t)keyi * a.ncols + col),
+                          (unsigned long long)(0 - (acc_lo[b] + ((uint64_t)acc_hi[b] << 32))));
         }
     }
 }
 cudaError_t launch_gemv(const GemvArgs &a, cudaStream_t s) {
-    const int coltiles = (a.ncols + 2 * GEMV_THREADS - 1) / (2 * GEMV_THREADS);
+    const int coltiles = (a.ncols + GEMV_THREADS - 1) / GEMV_THREADS;
     const int cttiles = (a.count + GEMV_TB - 1) / GEMV_TB;
     const int splits = (a.rows + a.rows_per_split - 1) / a.rows_per_split;
-    dim3 grid(coltiles, a.nkeys * cttiles, splits);
+    dim3 grid(cttiles, coltiles, a.nkeys * splits);
     gemv_kernel<<<grid, GEMV_THREADS, 0, s>>>(a);
     return cudaGetLastError();
 }

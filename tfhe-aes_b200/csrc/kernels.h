@@ -44,6 +44,7 @@ struct ConvertArgs {
     const double2 *tw;
     long npoly;
     int glwe_dim;
+    int levels;               // levels per GGSW (output slot order is reversed: slot 0 = last level)
 };
 struct GemvArgs {
     const uint16_t *digits;   // [count][rows] offset digits u = d + beta/2
