@@ -8,6 +8,7 @@
 #include "engine.h"
 
 int prepare_keys_from_device(tfa_ctx *ctx, const u64 *bsk_std_dev);  // engine.cu
+int alloc_key_staging(tfa_ctx *ctx);                                   // engine.cu
 
 __host__ __device__ static inline u64 mix64(u64 z) {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -122,6 +123,7 @@ extern "C" int tfa_client_keygen(tfa_ctx *ctx, uint64_t seed) {
     RC(tfa_ctx_alloc_keys(ctx));
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
+    RC(alloc_key_staging(ctx));
     const int n = ctx->n, k = ctx->k, big = ctx->big;
     ctx->h_lwe_sk.resize(n); ctx->h_glwe_sk.resize(big);
     for (int i = 0; i < n; i++) ctx->h_lwe_sk[i] = rnd(seed, 1, i) & 1;

@@ -58,7 +58,7 @@ extern "C" int tfa_ctx_create(const tfa_params *p, int device, void *stream, tfa
         g_create_error = "PBS (2^8, 5) and CBS (2^15, 1) decompositions are the compiled kernel variants (client.rs:42-43,51-52)";
         return TFA_ERR_PARAM;
     }
-    if (p->ks_base_log * p->ks_level > 63 || p->pfks_base_log * p->pfks_level > 63 || p->ks_base_log > 15 || p->pfks_base_log > 15) {
+    if (p->ks_base_log * p->ks_level > 63 || p->pfks_base_log * p->pfks_level > 63 || p->ks_base_log > 14 || p->pfks_base_log > 14) {
         g_create_error = "keyswitch decomposition out of range"; return TFA_ERR_PARAM;
     }
     if (p->lwe_dim < 1 || p->lwe_dim > 2048) { g_create_error = "lwe_dimension out of range"; return TFA_ERR_PARAM; }
@@ -80,7 +80,7 @@ extern "C" int tfa_ctx_create(const tfa_params *p, int device, void *stream, tfa
     ctx->profiling = false;
     ctx->own_stream = (stream == nullptr);
     ctx->stream = (cudaStream_t)stream;
-    ctx->bsk_f = nullptr; ctx->ksk = nullptr; ctx->pfpksk = nullptr; ctx->ksk_colsum = nullptr; ctx->pfpksk_colsum = nullptr;
+    ctx->bsk_f = nullptr; ctx->ksk = nullptr; ctx->pfpksk = nullptr; ctx->kp_ksk = nullptr; ctx->kp_pfpksk = nullptr;
     ctx->tw = nullptr; ctx->keys_allocated = ctx->keys_ready = false;
     ctx->d_lwe_sk = ctx->d_glwe_sk = nullptr;
     for (auto &l : ctx->lut_cache) l = nullptr;
@@ -103,7 +103,7 @@ extern "C" void tfa_ctx_destroy(tfa_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->bsk_f); cudaFree(ctx->ksk); cudaFree(ctx->pfpksk); cudaFree(ctx->ksk_colsum); cudaFree(ctx->pfpksk_colsum);
+    cudaFree(ctx->bsk_f); cudaFree(ctx->ksk); cudaFree(ctx->pfpksk); cudaFree(ctx->kp_ksk); cudaFree(ctx->kp_pfpksk);
     cudaFree(ctx->tw); cudaFree(ctx->d_lwe_sk); cudaFree(ctx->d_glwe_sk); cudaFree(ctx->ws);
     for (auto l : ctx->lut_cache) cudaFree(l);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -121,21 +121,17 @@ extern "C" int tfa_ctx_alloc_keys(tfa_ctx *ctx) {
     CU(cudaSetDevice(ctx->device));
     if (ctx->keys_allocated) return TFA_OK;
     CU(cudaMalloc(&ctx->bsk_f, ctx->bsk_f_bytes()));
-    CU(cudaMalloc(&ctx->ksk, ctx->ksk_bytes()));
-    CU(cudaMalloc(&ctx->pfpksk, ctx->pfpksk_bytes()));
-    CU(cudaMalloc(&ctx->ksk_colsum, (size_t)ctx->ks_cols_pad * 8));
-    CU(cudaMalloc(&ctx->pfpksk_colsum, (size_t)(ctx->k + 1) * ctx->gsz * 8));
+    CU(cudaMalloc(&ctx->kp_ksk, ctx->kp_ksk_bytes()));
+    CU(cudaMalloc(&ctx->kp_pfpksk, ctx->kp_pfpksk_bytes()));
     ctx->keys_allocated = true;
     return TFA_OK;
 }
 extern "C" int tfa_ctx_key_buffers(tfa_ctx *ctx, void **ptrs, size_t *bytes, int *count) {
     if (!ctx->keys_allocated) return ctx->fail(TFA_ERR_STATE, "key buffers not allocated");
     ptrs[0] = ctx->bsk_f; bytes[0] = ctx->bsk_f_bytes();
-    ptrs[1] = ctx->ksk; bytes[1] = ctx->ksk_bytes();
-    ptrs[2] = ctx->pfpksk; bytes[2] = ctx->pfpksk_bytes();
-    ptrs[3] = ctx->ksk_colsum; bytes[3] = (size_t)ctx->ks_cols_pad * 8;
-    ptrs[4] = ctx->pfpksk_colsum; bytes[4] = (size_t)(ctx->k + 1) * ctx->gsz * 8;
-    *count = 5;
+    ptrs[1] = ctx->kp_ksk; bytes[1] = ctx->kp_ksk_bytes();
+    ptrs[2] = ctx->kp_pfpksk; bytes[2] = ctx->kp_pfpksk_bytes();
+    *count = 3;
     return TFA_OK;
 }
 extern "C" int tfa_ctx_keys_ready(tfa_ctx *ctx) {
@@ -144,16 +140,24 @@ extern "C" int tfa_ctx_keys_ready(tfa_ctx *ctx) {
     return TFA_OK;
 }
 
-// finishes key preparation from standard-domain device buffers: bsk_std [n*l*(k+1)*(k+1) polys],
-// ksk already in padded layout in ctx->ksk, pfpksk already in ctx->pfpksk
+// standard-domain staging buffers for the two integer keys (freed again by prepare_keys_from_device)
+int alloc_key_staging(tfa_ctx *ctx) {
+    if (!ctx->ksk) CU(cudaMalloc(&ctx->ksk, ctx->ksk_bytes()));
+    if (!ctx->pfpksk) CU(cudaMalloc(&ctx->pfpksk, ctx->pfpksk_bytes()));
+    return TFA_OK;
+}
+// finishes key preparation from standard-domain device buffers: bsk_std [n*l*(k+1)*(k+1) polys] -> Fourier,
+// ctx->ksk (padded rows) and ctx->pfpksk -> int8-limb tensor layouts; the staging buffers are released
 int prepare_keys_from_device(tfa_ctx *ctx, const u64 *bsk_std_dev) {
     const long npoly = (long)ctx->n * ctx->p.pbs_level * (ctx->k + 1) * (ctx->k + 1);
     RC(dev_fourier(ctx, bsk_std_dev, npoly, ctx->p.pbs_level, ctx->bsk_f));
-    CU(launch_key_colsum(ctx->ksk, ctx->big * ctx->p.ks_level, ctx->ks_cols_pad, ctx->ks_cols_pad, 1, 0, ctx->ksk_colsum, ctx->stream));
-    const int prow = (ctx->big + 1) * ctx->p.pfks_level;
-    CU(launch_key_colsum(ctx->pfpksk, prow, ctx->gsz, ctx->gsz, ctx->k + 1, (size_t)prow * ctx->gsz, ctx->pfpksk_colsum, ctx->stream));
+    CU(launch_imma_prepare_key(ctx->ksk, 0, 1, ctx->ks_rows(), ctx->n + 1, ctx->ks_cols_pad, ctx->kp_ksk, ctx->stream));
+    CU(launch_imma_prepare_key(ctx->pfpksk, (size_t)ctx->pf_rows() * ctx->gsz, ctx->k + 1, ctx->pf_rows(), ctx->gsz, ctx->gsz, ctx->kp_pfpksk,
+                               ctx->stream));
     ctx->launches += 2;
     CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->ksk); cudaFree(ctx->pfpksk);
+    ctx->ksk = nullptr; ctx->pfpksk = nullptr;
     ctx->keys_ready = true;
     return TFA_OK;
 }
@@ -163,6 +167,7 @@ extern "C" int tfa_ctx_load_keys(tfa_ctx *ctx, const uint64_t *bsk, const uint64
     RC(tfa_ctx_alloc_keys(ctx));
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
+    RC(alloc_key_staging(ctx));
     const size_t bsk_bytes = (size_t)ctx->n * ctx->p.pbs_level * (ctx->k + 1) * ctx->gsz * 8;
     u64 *tmp = nullptr;
     CU(cudaMalloc(&tmp, bsk_bytes));
@@ -192,50 +197,52 @@ int dev_fourier(tfa_ctx *ctx, const u64 *polys, long npoly, int levels, double2 
     return TFA_OK;
 }
 
-static int rows_per_split(int rows, int base_ctas) {
-    // aim for >= ~2 waves of CTAs (2 resident per SM); splits in whole chunks of 256 rows
-    int want = (4 * 148 + base_ctas - 1) / base_ctas;
-    if (want < 1) want = 1;
-    int chunks = (rows + 255) / 256;
-    if (want > chunks) want = chunks;
-    int per = (chunks + want - 1) / want;
-    return per * 256;
-}
-
 // out = (0,..,0,b) - sum_i sum_l d_{i,l} KSK[i][l]
 int dev_keyswitch(tfa_ctx *ctx, const u64 *in, int count, u64 *out) {
-    const int rows = ctx->big * ctx->p.ks_level, np = ctx->n + 1;
-    WS(digits, uint16_t, (size_t)count * rows);
+    const int np = ctx->n + 1, rows_pad = ctx->ks_kchunks() * 32;
+    const int limbs = ctx->p.ks_base_log > 6 ? 2 : 1;  // digits in [-beta/2, beta/2]: one s8 limb holds [-64, 63]
+    WS(dl, int8_t, (size_t)count * rows_pad);
+    int8_t *dh = nullptr;
+    if (limbs == 2) { dh = ws_get<int8_t>(ctx, (size_t)count * rows_pad); if (!dh) return TFA_ERR_STATE; }
     {
         StageTimer t(ctx, ST_KS_DECOMP);
-        CU(launch_decompose(in, ctx->lw, ctx->big, count, ctx->p.ks_base_log, ctx->p.ks_level, digits, ctx->stream));
+        if (rows_pad != ctx->ks_rows()) {
+            CU(cudaMemsetAsync(dl, 0, (size_t)count * rows_pad, ctx->stream));
+            if (dh) CU(cudaMemsetAsync(dh, 0, (size_t)count * rows_pad, ctx->stream));
+        }
+        CU(launch_imma_decompose(in, ctx->lw, ctx->big, count, ctx->p.ks_base_log, ctx->p.ks_level, rows_pad, dl, dh, ctx->stream));
     }
     StageTimer t(ctx, ST_KS_GEMV);
-    CU(launch_gemv_init(out, np, np, count, ctx->ksk_colsum, 1ull << (ctx->p.ks_base_log - 1), in, ctx->lw, ctx->big, ctx->n, ctx->stream));
-    GemvArgs g{};
-    g.digits = digits; g.key = ctx->ksk; g.out = out; g.key_stride = 0; g.key_row_stride = ctx->ks_cols_pad;
-    g.out_stride = np; g.rows = rows; g.ncols = np; g.nkeys = 1; g.count = count;
-    g.rows_per_split = rows_per_split(rows, ((np + 255) / 256) * ((count + 31) / 32));
-    CU(launch_gemv(g, ctx->stream));
+    CU(launch_gemv_init(out, np, np, count, nullptr, 0, in, ctx->lw, ctx->big, ctx->n, ctx->stream));
+    ImmaGemvArgs g{};
+    g.dl = dl; g.dh = dh; g.kp = ctx->kp_ksk; g.out = out; g.out_stride = np; g.rows_pad = rows_pad;
+    g.kchunks = ctx->ks_kchunks(); g.ntiles = ctx->ks_ntiles(); g.ncols = np; g.nkeys = 1; g.count = count;
+    CU(launch_imma_gemv(g, limbs, ctx->stream));
     ctx->launches += 3;
     return TFA_OK;
 }
 
 // for every key r: glwe_r = - sum_j sum_l d_{j,l} PFPKSK_r[j][l]; out[b][r][gsz] with stride
 int dev_pfks(tfa_ctx *ctx, const u64 *in, int count, u64 *out, int out_stride) {
-    const int rows = (ctx->big + 1) * ctx->p.pfks_level, kp1 = ctx->k + 1;
-    WS(digits, uint16_t, (size_t)count * rows);
+    const int kp1 = ctx->k + 1, rows_pad = ctx->pf_kchunks() * 32;
+    const int limbs = ctx->p.pfks_base_log > 6 ? 2 : 1;
+    WS(dl, int8_t, (size_t)count * rows_pad);
+    int8_t *dh = nullptr;
+    if (limbs == 2) { dh = ws_get<int8_t>(ctx, (size_t)count * rows_pad); if (!dh) return TFA_ERR_STATE; }
     {
         StageTimer t(ctx, ST_PFKS_DECOMP);
-        CU(launch_decompose(in, ctx->lw, ctx->big + 1, count, ctx->p.pfks_base_log, ctx->p.pfks_level, digits, ctx->stream));
+        if (rows_pad != ctx->pf_rows()) {
+            CU(cudaMemsetAsync(dl, 0, (size_t)count * rows_pad, ctx->stream));
+            if (dh) CU(cudaMemsetAsync(dh, 0, (size_t)count * rows_pad, ctx->stream));
+        }
+        CU(launch_imma_decompose(in, ctx->lw, ctx->big + 1, count, ctx->p.pfks_base_log, ctx->p.pfks_level, rows_pad, dl, dh, ctx->stream));
     }
     StageTimer t(ctx, ST_PFKS_GEMV);
-    CU(launch_gemv_init(out, out_stride, kp1 * ctx->gsz, count, ctx->pfpksk_colsum, 1ull << (ctx->p.pfks_base_log - 1), nullptr, 0, 0, 0, ctx->stream));
-    GemvArgs g{};
-    g.digits = digits; g.key = ctx->pfpksk; g.out = out; g.key_stride = (size_t)rows * ctx->gsz; g.key_row_stride = ctx->gsz;
-    g.out_stride = out_stride; g.rows = rows; g.ncols = ctx->gsz; g.nkeys = kp1; g.count = count;
-    g.rows_per_split = rows_per_split(rows, ((ctx->gsz + 255) / 256) * ((count + 31) / 32) * kp1);
-    CU(launch_gemv(g, ctx->stream));
+    CU(launch_gemv_init(out, out_stride, kp1 * ctx->gsz, count, nullptr, 0, nullptr, 0, 0, 0, ctx->stream));
+    ImmaGemvArgs g{};
+    g.dl = dl; g.dh = dh; g.kp = ctx->kp_pfpksk; g.out = out; g.out_stride = out_stride; g.rows_pad = rows_pad;
+    g.kchunks = ctx->pf_kchunks(); g.ntiles = ctx->pf_ntiles(); g.ncols = ctx->gsz; g.nkeys = kp1; g.count = count;
+    CU(launch_imma_gemv(g, limbs, ctx->stream));
     ctx->launches += 3;
     return TFA_OK;
 }

@@ -21,10 +21,10 @@ struct tfa_ctx {
 
     // prepared keys (device)
     double2 *bsk_f;        // [n][pbs_level][k+1][k+1][256]
-    u64 *ksk;              // [big*ks_level][ks_cols_pad]
-    u64 *pfpksk;           // [k+1][(big+1)*pfks_level][gsz]
-    u64 *ksk_colsum;       // [ks_cols_pad]
-    u64 *pfpksk_colsum;    // [(k+1)*gsz]
+    uint8_t *kp_ksk;       // keyswitch key, int8-limb tensor layout [ntiles][kchunks][2048]   (imma_kernels.cu)
+    uint8_t *kp_pfpksk;    // PFPKSK list, same layout [k+1][ntiles][kchunks][2048]
+    u64 *ksk;              // standard-domain staging, only alive during key preparation: [big*ks_level][ks_cols_pad]
+    u64 *pfpksk;           //   [k+1][(big+1)*pfks_level][gsz]
     double2 *tw;           // 512 twiddles
     int ks_cols_pad;
     bool keys_allocated, keys_ready;
@@ -47,6 +47,14 @@ struct tfa_ctx {
 
     size_t bsk_f_bytes() const { return (size_t)n * p.pbs_level * (k + 1) * 256 * (k + 1) * sizeof(double2); }
     size_t ksk_bytes() const { return (size_t)big * p.ks_level * ks_cols_pad * 8; }
+    int ks_rows() const { return big * (int)p.ks_level; }
+    int pf_rows() const { return (big + 1) * (int)p.pfks_level; }
+    int ks_kchunks() const { return (ks_rows() + 31) / 32; }
+    int pf_kchunks() const { return (pf_rows() + 31) / 32; }
+    int ks_ntiles() const { return (n + 1 + 7) / 8; }
+    int pf_ntiles() const { return (gsz + 7) / 8; }
+    size_t kp_ksk_bytes() const { return (size_t)ks_ntiles() * ks_kchunks() * 2048; }
+    size_t kp_pfpksk_bytes() const { return (size_t)(k + 1) * pf_ntiles() * pf_kchunks() * 2048; }
     size_t pfpksk_bytes() const { return (size_t)(k + 1) * (big + 1) * p.pfks_level * gsz * 8; }
     size_t byte_words() const { return (size_t)8 * lw; }
 

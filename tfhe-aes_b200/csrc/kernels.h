@@ -46,19 +46,25 @@ struct ConvertArgs {
     int glwe_dim;
     int levels;               // levels per GGSW (output slot order is reversed: slot 0 = last level)
 };
-struct GemvArgs {
-    const uint16_t *digits;   // [count][rows] offset digits u = d + beta/2
-    const uint64_t *key;      // [nkeys][rows][ncols]
-    uint64_t *out;            // [count][nkeys*ncols (+pad)]
-    size_t key_stride;        // words between keys
-    int key_row_stride;       // words between key rows (>= ncols, even)
-    int out_stride;           // words between ciphertexts in out
-    int rows;
+
+struct ImmaGemvArgs {
+    const int8_t *dl;         // [count][rows_pad] low digit limbs
+    const int8_t *dh;         // [count][rows_pad] high digit limbs (nullptr when digits fit one limb)
+    const uint8_t *kp;        // prepared key [nkeys][ntiles][kchunks][2048]
+    uint64_t *out;            // [count][out_stride], pre-initialised; the product is subtracted
+    int out_stride;
+    int rows_pad;             // kchunks * 32
+    int kchunks;
+    int ntiles;               // ceil(ncols / 8)
     int ncols;
     int nkeys;
     int count;
-    int rows_per_split;
 };
+cudaError_t launch_imma_prepare_key(const uint64_t *key, size_t key_stride, int nkeys, int rows, int ncols, int row_stride, uint8_t *kp,
+                                    cudaStream_t s);
+cudaError_t launch_imma_decompose(const uint64_t *in, int in_stride, int nelem, int count, int base_log, int levels, int rows_pad,
+                                  int8_t *dl, int8_t *dh, cudaStream_t s);
+cudaError_t launch_imma_gemv(const ImmaGemvArgs &a, int digit_limbs, cudaStream_t s);
 
 cudaError_t launch_pbs(int K, int G, int base_log, int levels, const PbsArgs &a, cudaStream_t s);
 cudaError_t launch_vp(int K, int G, int base_log, int levels, const VpArgs &a, cudaStream_t s);
@@ -66,11 +72,6 @@ cudaError_t launch_cmux_tree(int K, int G, int base_log, int levels, const TreeA
 cudaError_t launch_fourier_convert(const ConvertArgs &a, cudaStream_t s);
 
 // integer kernels (int_kernels.cu)
-cudaError_t launch_decompose(const uint64_t *in, int in_stride, int nelem, int count, int base_log, int levels,
-                             uint16_t *digits, cudaStream_t s);
-cudaError_t launch_gemv(const GemvArgs &a, cudaStream_t s);
-cudaError_t launch_key_colsum(const uint64_t *key, int rows, int ncols, int row_stride, int nkeys, size_t key_stride,
-                              uint64_t *sums, cudaStream_t s);
 // out[b][c] = offset*colsum[c] (+ body of in for the keyswitch when body_src != nullptr)
 cudaError_t launch_gemv_init(uint64_t *out, int out_stride, int total_cols, int count, const uint64_t *colsum,
                              uint64_t offset, const uint64_t *body_src, int body_src_stride, int body_src_index,
