@@ -116,6 +116,34 @@ HD void phase_load_decompose(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg, co
         rg.v[n1] = cmk((double)d0, (double)d1);
     }
 }
+// register-only forms used by the warp-specialised PBS kernel (no Fourier accumulators in the FFT warps)
+template <int BASE_LOG, int LEVELS>
+HD void load_decompose_rot(const uint64_t *poly, int lane, int rot, cd (&v)[16], uint32_t (&st_re)[16], uint32_t (&st_im)[16]) {
+    const int s0 = (lane - rot) & (2 * POLY_N - 1);
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) {
+        const int j = 16 * n1 + lane;
+        const int s = (s0 + 16 * n1) & (2 * POLY_N - 1);
+        const int i0 = s & (POLY_N - 1);
+        const uint64_t x0 = poly[i0], x1 = poly[i0 ^ POLY_M];
+        const uint64_t m0 = (uint64_t)0 - (uint64_t)((s >> 9) & 1);
+        const uint64_t m1 = (uint64_t)0 - (uint64_t)(((s >> 9) ^ (s >> 8)) & 1);
+        const uint64_t a0 = ((x0 ^ m0) - m0) - poly[j];
+        const uint64_t a1 = ((x1 ^ m1) - m1) - poly[j + POLY_M];
+        const int d0 = decomp_first<BASE_LOG, LEVELS>(a0, st_re[n1]);
+        const int d1 = decomp_first<BASE_LOG, LEVELS>(a1, st_im[n1]);
+        v[n1] = cmk((double)d0, (double)d1);
+    }
+}
+template <int BASE_LOG>
+HD void next_digits(cd (&v)[16], uint32_t (&st_re)[16], uint32_t (&st_im)[16]) {
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) {
+        const int d0 = decomp_next<BASE_LOG>(st_re[n1]);
+        const int d1 = decomp_next<BASE_LOG>(st_im[n1]);
+        v[n1] = cmk((double)d0, (double)d1);
+    }
+}
 // digits of the next level (level index decreasing)
 template <int K, int G, int BASE_LOG>
 HD void phase_next_digits(int tid, CmuxRegs<K, G> &rg) {
@@ -128,25 +156,33 @@ HD void phase_next_digits(int tid, CmuxRegs<K, G> &rg) {
     }
 }
 // ---- forward FFT of the digit polynomial held in v -------------------------------------------
+// The *_b variants take the base of a [16][XB_ELEMS] exchange / hand-over buffer and the twiddle table
+// explicitly (the warp-specialised PBS kernel double-buffers it); the CmuxSmem forms use sm.xb.
 template <int K, int G>
-HD void phase_fwd1(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) {
+HD void phase_fwd1_b(int tid, cd (*xb)[XB_ELEMS], const cd *twf, cd (&v)[16]) {
     const int gid = tid >> 4, lane = tid & 15;
     if (gid >= G * (K + 1)) return;
-    fft256_fwd_pass1(rg.v, lane, sm.twf, sm.xb[gid]);
+    fft256_fwd_pass1(v, lane, twf, xb[gid]);
 }
 template <int K, int G>
-HD void phase_fwd2(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) {
+HD void phase_fwd2_b(int tid, cd (*xb)[XB_ELEMS], cd (&v)[16]) {
     const int gid = tid >> 4, lane = tid & 15;
     if (gid >= G * (K + 1)) return;
-    fft256_fwd_pass2(rg.v, lane, sm.xb[gid]);
+    fft256_fwd_pass2(v, lane, xb[gid]);
 }
 template <int K, int G>
-HD void phase_fwd3(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) {
+HD void phase_fwd3_b(int tid, cd (*xb)[XB_ELEMS], cd (&v)[16]) {
     const int gid = tid >> 4, lane = tid & 15;
     if (gid >= G * (K + 1)) return;
 #pragma unroll
-    for (int k2 = 0; k2 < 16; k2++) sm.xb[gid][lane + 16 * k2] = rg.v[rev4(k2)];
+    for (int k2 = 0; k2 < 16; k2++) xb[gid][lane + 16 * k2] = v[rev4(k2)];
 }
+template <int K, int G>
+HD void phase_fwd1(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) { phase_fwd1_b<K, G>(tid, sm.xb, sm.twf, rg.v); }
+template <int K, int G>
+HD void phase_fwd2(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) { phase_fwd2_b<K, G>(tid, sm.xb, rg.v); }
+template <int K, int G>
+HD void phase_fwd3(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) { phase_fwd3_b<K, G>(tid, sm.xb, rg.v); }
 // ---- multiply-accumulate of one level against the Fourier GGSW -------------------------------
 // ggsw_level points at [row r][col c][point p] complex of this level.
 template <int K, int G>
@@ -213,33 +249,40 @@ HD void phase_inv0(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) {
         for (int c = 0; c <= K; c++) sm.xb[ct * (K + 1) + c][p] = rg.facc[ct][c];
 }
 template <int K, int G>
-HD void phase_inv1(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) {
+HD void phase_inv1_b(int tid, cd (*xb)[XB_ELEMS], cd (&v)[16]) {
     const int gid = tid >> 4, lane = tid & 15;
     if (gid >= G * (K + 1)) return;
 #pragma unroll
-    for (int k2 = 0; k2 < 16; k2++) rg.v[k2] = sm.xb[gid][lane + 16 * k2];
-    fft256_inv_pass1_compute(rg.v);
+    for (int k2 = 0; k2 < 16; k2++) v[k2] = xb[gid][lane + 16 * k2];
+    fft256_inv_pass1_compute(v);
 }
 template <int K, int G>
-HD void phase_inv2(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) {
+HD void phase_inv2_b(int tid, cd (*xb)[XB_ELEMS], const cd *twi, cd (&v)[16]) {
     const int gid = tid >> 4, lane = tid & 15;
     if (gid >= G * (K + 1)) return;
-    fft256_inv_pass1_store(rg.v, lane, sm.twi, sm.xb[gid]);
+    fft256_inv_pass1_store(v, lane, twi, xb[gid]);
 }
+// acc: base of the [G][K+1][512] accumulator array
 template <int K, int G>
-HD void phase_inv3(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) {
+HD void phase_inv3_b(int tid, cd (*xb)[XB_ELEMS], uint64_t (*acc)[K + 1][POLY_N], cd (&v)[16]) {
     const int gid = tid >> 4, lane = tid & 15;
     if (gid >= G * (K + 1)) return;
     const int ct = gid / (K + 1), c = gid % (K + 1);
-    fft256_inv_pass2(rg.v, lane, sm.xb[gid]);
-    uint64_t *poly = sm.acc[ct][c];
+    fft256_inv_pass2(v, lane, xb[gid]);
+    uint64_t *poly = acc[ct][c];
 #pragma unroll
     for (int n1 = 0; n1 < 16; n1++) {
         const int j = 16 * n1 + lane;
-        poly[j] += f64_to_torus(rg.v[n1].x);
-        poly[j + POLY_M] += f64_to_torus(rg.v[n1].y);
+        poly[j] += f64_to_torus(v[n1].x);
+        poly[j + POLY_M] += f64_to_torus(v[n1].y);
     }
 }
+template <int K, int G>
+HD void phase_inv1(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) { phase_inv1_b<K, G>(tid, sm.xb, rg.v); }
+template <int K, int G>
+HD void phase_inv2(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) { phase_inv2_b<K, G>(tid, sm.xb, sm.twi, rg.v); }
+template <int K, int G>
+HD void phase_inv3(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) { phase_inv3_b<K, G>(tid, sm.xb, sm.acc, rg.v); }
 
 // ---- forward transform of a torus polynomial (key conversion) -----------------
 // lane loads 32 coefficients as signed 64-bit -> f64 (53-bit rounding)

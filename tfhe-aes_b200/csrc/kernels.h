@@ -67,6 +67,7 @@ cudaError_t launch_imma_decompose(const uint64_t *in, int in_stride, int nelem, 
 cudaError_t launch_imma_gemv(const ImmaGemvArgs &a, int digit_limbs, cudaStream_t s);
 
 cudaError_t launch_pbs(int K, int G, int base_log, int levels, const PbsArgs &a, cudaStream_t s);
+cudaError_t launch_pbs_ws(int K, int G, int base_log, int levels, const PbsArgs &a, cudaStream_t s);
 cudaError_t launch_vp(int K, int G, int base_log, int levels, const VpArgs &a, cudaStream_t s);
 cudaError_t launch_cmux_tree(int K, int G, int base_log, int levels, const TreeArgs &a, cudaStream_t s);
 cudaError_t launch_fourier_convert(const ConvertArgs &a, cudaStream_t s);
