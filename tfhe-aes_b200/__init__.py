@@ -11,3 +11,4 @@ from .binding import (  # noqa: F401
     SBOX, INV_SBOX, mul2, mul3, mul9, mul11, mul13, mul14,
 )
 from .server import Server, sbox, many_sbox, many_wopbs_without_padding  # noqa: F401
+from . import sharding  # noqa: F401
