@@ -91,6 +91,18 @@ HD void fft256_fwd_pass1(cd (&v)[16], int lane, const cd *twf, cd *xb) {
 #pragma unroll
     for (int k1 = 0; k1 < 16; k1++) xb[k1 * XB_STRIDE + lane] = cmul(v[rev4(k1)], twf[k1 * 16 + lane]);
 }
+// the same in two halves, so that the arithmetic can be scheduled before the exchange buffer is free
+HD void fft256_fwd_pass1_compute(cd (&v)[16], int lane, const cd *twf) {
+#pragma unroll
+    for (int n1 = 1; n1 < 16; n1++) v[n1] = mul_w64<1>(v[n1], n1);
+    fft16<1>(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) v[rev4(k1)] = cmul(v[rev4(k1)], twf[k1 * 16 + lane]);
+}
+HD void fft256_fwd_pass1_store(const cd (&v)[16], int lane, cd *xb) {
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) xb[k1 * XB_STRIDE + lane] = v[rev4(k1)];
+}
 // lane = k1.  Out: X[lane + 16 k2] at v[rev4(k2)]
 HD void fft256_fwd_pass2(cd (&v)[16], int lane, const cd *xb) {
 #pragma unroll

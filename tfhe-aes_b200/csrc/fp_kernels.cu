@@ -141,7 +141,6 @@ __global__ void __launch_bounds__(CMUX_THREADS, 1) pbs_kernel(PbsArgs a) {
         phase_load_decompose<K, G, BASE_LOG, LEVELS, DIFF_ROTATE>(tid, sm, rg, nullptr);
 #pragma unroll 1
         for (int lev = LEVELS; lev >= 1; lev--) {
-            if (lev != LEVELS) phase_next_digits<K, G, BASE_LOG>(tid, rg);
             phase_fwd1<K, G>(tid, sm, rg);
             __syncwarp();
             phase_fwd2<K, G>(tid, sm, rg);
@@ -155,6 +154,9 @@ __global__ void __launch_bounds__(CMUX_THREADS, 1) pbs_kernel(PbsArgs a) {
                 rd_off += ROW_BYTES;
                 if (rd_off == RING_BYTES) rd_off = 0;
                 issue();
+                // the digits of the next level (integer + conversion pipes) are extracted in the shadow of the
+                // multiply-accumulate (FP64 pipe): v is free during this phase
+                if (r == 0 && lev > 1) phase_next_digits<K, G, BASE_LOG>(tid, rg);
             }
             __syncthreads();
         }
