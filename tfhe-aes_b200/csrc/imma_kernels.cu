@@ -110,8 +110,8 @@ __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src
 
 // CTA: 128 bits x (8*NT) columns of one key, all rows.  DL = digit limbs (1: KS, 2: PFKS).
 template <int NT, int DL>
-__global__ void __launch_bounds__(IG_THREADS, 2) imma_gemv_kernel(ImmaGemvArgs a) {
-    __shared__ __align__(16) uint8_t kbuf[2][NT][IG_CHUNK_BYTES];
+__global__ void __launch_bounds__(IG_THREADS, (NT * DL >= 4) ? 1 : 2) imma_gemv_kernel(ImmaGemvArgs a) {
+    __shared__ __align__(16) uint8_t kbuf[3][NT][IG_CHUNK_BYTES];   // 3-stage ring: one barrier per 32-row chunk
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int m0 = blockIdx.x * IG_MTILE + warp * 16;
     const int nt0 = blockIdx.y * NT;
@@ -133,35 +133,42 @@ __global__ void __launch_bounds__(IG_THREADS, 2) imma_gemv_kernel(ImmaGemvArgs a
     const int8_t *dh0 = DL == 2 ? a.dh + (size_t)(ok0 ? m0 + g : 0) * a.rows_pad + 4 * t : nullptr;
     const int8_t *dh1 = DL == 2 ? a.dh + (size_t)(ok1 ? m0 + g + 8 : 0) * a.rows_pad + 4 * t : nullptr;
     auto fill = [&](int buf, int kc) {
-        // NT chunks of 2 KB = NT*128 transfers of 16 B
-        for (int i = tid; i < NT * 128; i += IG_THREADS) {
-            const int n = i >> 7, off = (i & 127) * 16;
-            const bool valid = (nt0 + n) < a.ntiles;
-            cp_async_16(&kbuf[buf][n][off], kp + ((size_t)(valid ? n : 0) * a.kchunks + kc) * IG_CHUNK_BYTES + off);
+        if (kc < a.kchunks) {
+            for (int i = tid; i < NT * 128; i += IG_THREADS) {  // NT chunks of 2 KB = NT*128 transfers of 16 B
+                const int n = i >> 7, off = (i & 127) * 16;
+                const bool valid = (nt0 + n) < a.ntiles;
+                cp_async_16(&kbuf[buf][n][off], kp + ((size_t)(valid ? n : 0) * a.kchunks + kc) * IG_CHUNK_BYTES + off);
+            }
         }
         asm volatile("cp.async.commit_group;\n" ::);
     };
-    fill(0, 0);
-    for (int kc = 0; kc < a.kchunks; kc++) {
-        const int buf = kc & 1;
-        if (kc + 1 < a.kchunks) fill(buf ^ 1, kc + 1);
-        else asm volatile("cp.async.commit_group;\n" ::);
-        uint32_t af[DL][4];
-        {
-            const int o = kc * 32;
-            af[0][0] = ok0 ? __ldg(reinterpret_cast<const uint32_t *>(dl0 + o)) : 0;
-            af[0][1] = ok1 ? __ldg(reinterpret_cast<const uint32_t *>(dl1 + o)) : 0;
-            af[0][2] = ok0 ? __ldg(reinterpret_cast<const uint32_t *>(dl0 + o + 16)) : 0;
-            af[0][3] = ok1 ? __ldg(reinterpret_cast<const uint32_t *>(dl1 + o + 16)) : 0;
-            if (DL == 2) {
-                af[DL - 1][0] = ok0 ? __ldg(reinterpret_cast<const uint32_t *>(dh0 + o)) : 0;
-                af[DL - 1][1] = ok1 ? __ldg(reinterpret_cast<const uint32_t *>(dh1 + o)) : 0;
-                af[DL - 1][2] = ok0 ? __ldg(reinterpret_cast<const uint32_t *>(dh0 + o + 16)) : 0;
-                af[DL - 1][3] = ok1 ? __ldg(reinterpret_cast<const uint32_t *>(dh1 + o + 16)) : 0;
-            }
+    auto load_a = [&](uint32_t (&af)[DL][4], int kc) {   // A fragments (digits) of chunk kc straight from global / L2
+        const int o = kc * 32;
+        af[0][0] = ok0 ? __ldg(reinterpret_cast<const uint32_t *>(dl0 + o)) : 0;
+        af[0][1] = ok1 ? __ldg(reinterpret_cast<const uint32_t *>(dl1 + o)) : 0;
+        af[0][2] = ok0 ? __ldg(reinterpret_cast<const uint32_t *>(dl0 + o + 16)) : 0;
+        af[0][3] = ok1 ? __ldg(reinterpret_cast<const uint32_t *>(dl1 + o + 16)) : 0;
+        if (DL == 2) {
+            af[DL - 1][0] = ok0 ? __ldg(reinterpret_cast<const uint32_t *>(dh0 + o)) : 0;
+            af[DL - 1][1] = ok1 ? __ldg(reinterpret_cast<const uint32_t *>(dh1 + o)) : 0;
+            af[DL - 1][2] = ok0 ? __ldg(reinterpret_cast<const uint32_t *>(dh0 + o + 16)) : 0;
+            af[DL - 1][3] = ok1 ? __ldg(reinterpret_cast<const uint32_t *>(dh1 + o + 16)) : 0;
         }
-        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-        __syncthreads();
+    };
+    fill(0, 0);
+    fill(1, 1);
+    uint32_t af[DL][4], af_next[DL][4];
+    load_a(af_next, 0);
+    for (int kc = 0; kc < a.kchunks; kc++) {
+#pragma unroll
+        for (int l = 0; l < DL; l++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) af[l][e] = af_next[l][e];
+        if (kc + 1 < a.kchunks) load_a(af_next, kc + 1);       // in flight while this chunk's MMAs run
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");   // chunk kc has landed
+        __syncthreads();                                         // ... for everyone, and chunk kc-1 is consumed
+        fill((kc + 2) % 3, kc + 2);
+        const int buf = kc % 3;
 #pragma unroll
         for (int n = 0; n < NT; n++) {
 #pragma unroll
@@ -174,7 +181,6 @@ __global__ void __launch_bounds__(IG_THREADS, 2) imma_gemv_kernel(ImmaGemvArgs a
                 }
             }
         }
-        __syncthreads();
     }
     // epilogue: recombine the limb partial sums (u64 wrapping) and subtract from the output
 #pragma unroll
@@ -197,7 +203,9 @@ __global__ void __launch_bounds__(IG_THREADS, 2) imma_gemv_kernel(ImmaGemvArgs a
     }
 }
 cudaError_t launch_imma_gemv(const ImmaGemvArgs &a, int digit_limbs, cudaStream_t s) {
-    if (digit_limbs == 2) {  // 64 accumulator registers per column tile: one tile per CTA keeps 2 CTAs per SM
+    if (digit_limbs == 2) {
+        // 128 bits x 8 columns per CTA, 2 CTAs per SM (a 16-column tile with one CTA per SM measured slower:
+        // 18.5 vs 15.4 ms per 3072 bits)
         if (!a.dh) return cudaErrorInvalidValue;
         dim3 grid((a.count + IG_MTILE - 1) / IG_MTILE, a.ntiles, a.nkeys);
         imma_gemv_kernel<1, 2><<<grid, IG_THREADS, 0, s>>>(a);
