@@ -90,6 +90,7 @@ def cpu_sample(evals_per_thread=1, threads=None):
     cts = o.encrypt_bytes(bytes(i % 256 for i in range(threads)))
 
     def work(i):
+        orc.lib().orc_set_threads(1)                        # OpenMP ICVs are per thread: pin every worker to one
         for _ in range(evals_per_thread):
             out = o.many_sbox(cts[i], False)        # ctypes releases the GIL during the call
         return out
@@ -119,7 +120,7 @@ def run_reference(args):
     v = float(np.mean([r["blocks_per_s"] for r in vals]))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup_ref,
             "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64+f64", "data": "synthetic",
-            "config": {"workload": "aes128_ctr PARAM_OPT, CPU port of the reference path (oracle), bounded sample scaled by WoPBS count",
+            "config": {"workload": f"aes128_ctr (add_scalar + aes_encrypt = {WOPBS_PER_BLOCK} byte-WoPBS = {PBS_PER_BLOCK} PBS per block), PARAM_OPT n=669 k=4 N=512; CPU port of the reference path (oracle), bounded sample scaled by the WoPBS count",
                        "note": "the Rust reference (tfhe-rs 0.11.2) cannot be built in this image; README.md:186 quotes 84 s/block/core"},
             "sbox_evals_per_s": float(np.mean([r["evals_per_s"] for r in vals])),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": vals[0]["threads"], "kind": "port", "sample": vals[0]["sample"]},

@@ -354,3 +354,52 @@ def test_opt_config1_ctr_block(pkg, engine_opt, oracle_opt):
     dec = srv.aes_decrypt(rk, out)
     assert o.decrypt_bytes(dec[0]) == (255).to_bytes(16, "big")
     assert o.decrypt_bytes(dec[1]) == (256).to_bytes(16, "big")
+
+
+# ---- boundary behaviour ---------------------------------------------------------------------------------------
+def test_error_behaviour(pkg, engine_test):
+    """The reference panics on misuse; the C ABI returns a status and a message."""
+    e = pkg.Engine(pkg.param_test())
+    with pytest.raises(pkg.TfaError) as ei:        # keys not loaded
+        e.sbox(np.zeros((1, 8, e.lw), dtype=np.uint64))
+    assert ei.value.code == 3
+    e.close()
+    with pytest.raises(pkg.TfaError) as ei:        # empty batch
+        engine_test.many_wopbs(np.zeros((0, 8, engine_test.lw), dtype=np.uint64), np.zeros((1, 8, 512), dtype=np.uint64))
+    assert ei.value.code == 1
+
+
+def test_config4_decrypt_16_blocks(pkg, engine_test, oracle_test, orc):
+    """BASELINE config 4 shape on the small parameter set: aes_decrypt on 16 CTR blocks."""
+    o = oracle_test
+    srv = pkg.Server(engine_test)
+    key = bytes(range(16, 32))
+    rk = srv.aes_key_expansion(o.encrypt_bytes(key))
+    iv = 2 ** 64 - 3
+    blocks = [orc.clear_aes_encrypt(key, ((iv + i) % 2 ** 128).to_bytes(16, "big")) for i in range(16)]
+    states = np.stack([o.encrypt_bytes(b) for b in blocks])
+    dec = srv.aes_decrypt(rk, states)
+    for i in range(16):
+        assert o.decrypt_bytes(dec[i]) == ((iv + i) % 2 ** 128).to_bytes(16, "big")
+
+
+def test_ragged_batches(pkg, engine_test, oracle_test):
+    """Batch sizes that are not multiples of any tile (ciphertexts per CTA, 16-bit MMA rows, 128-bit tiles)."""
+    o = oracle_test
+    for nct in (1, 3, 17):
+        data = bytes((37 * i + nct) % 256 for i in range(nct))
+        got = engine_test.sbox(o.encrypt_bytes(data), False)
+        assert o.decrypt_bytes(got) == bytes(pkg.SBOX[b] for b in data)
+
+
+@pytest.mark.slow
+def test_cli_mirrors_reference_driver(pkg):
+    """tfhe_aes_cli = src/main.rs on the engine (PARAM_OPT): keygen, key expansion, CTR, decrypt + verify."""
+    import os
+    import subprocess
+    cli = os.path.join(os.path.dirname(pkg.lib_path()), "tfhe_aes_cli")
+    if not os.path.exists(cli):
+        pytest.skip("CLI not built")
+    r = subprocess.run([cli, "--number-of-outputs", "3", "--iv", "254", "--key", "12345678901234567890"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Passed" in r.stdout and "AES key expansion took" in r.stdout

@@ -138,6 +138,7 @@ static int sbox_like_dev(tfa_ctx *ctx, const u64 *in, int nct, int which, u64 *o
 }
 extern "C" int tfa_sbox(tfa_ctx *ctx, uint64_t *bytes, int nct, int inv) {
     Guard g(ctx);
+    if (nct < 1) return ctx->fail(TFA_ERR_PARAM, "nct must be >= 1");
     RC(require_keys(ctx));
     const size_t w = (size_t)nct * ctx->byte_words();
     const int nb = nblocks_per_byte(ctx);
@@ -151,6 +152,7 @@ extern "C" int tfa_sbox(tfa_ctx *ctx, uint64_t *bytes, int nct, int inv) {
 }
 extern "C" int tfa_many_sbox(tfa_ctx *ctx, const uint64_t *bytes_in, int nct, int inv, uint64_t *out) {
     Guard g(ctx);
+    if (nct < 1) return ctx->fail(TFA_ERR_PARAM, "nct must be >= 1");
     RC(require_keys(ctx));
     const int L = inv ? 4 : 3, nb = nblocks_per_byte(ctx);
     const size_t w = (size_t)nct * ctx->byte_words();
@@ -351,18 +353,21 @@ static size_t add_scalar_scratch(const tfa_ctx *ctx, int nblk) {
 // ---- device-pointer entry points -----------------------------------------------------------------
 extern "C" int tfa_aes_encrypt_dev(tfa_ctx *ctx, const uint64_t *rk, uint64_t *states, int nblk) {
     Guard g(ctx);
+    if (nblk < 1) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1");
     RC(require_keys(ctx));
     RC(ws_reserve(ctx, aes_scratch(ctx, nblk, 3)));
     return aes_encrypt_nolock(ctx, rk, states, nblk);
 }
 extern "C" int tfa_aes_decrypt_dev(tfa_ctx *ctx, const uint64_t *rk, uint64_t *states, int nblk) {
     Guard g(ctx);
+    if (nblk < 1) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1");
     RC(require_keys(ctx));
     RC(ws_reserve(ctx, aes_scratch(ctx, nblk, 5)));
     return aes_decrypt_nolock(ctx, rk, states, nblk);
 }
 extern "C" int tfa_aes_round_dev(tfa_ctx *ctx, const uint64_t *rk_round, uint64_t *states, int nblk) {
     Guard g(ctx);
+    if (nblk < 1) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1");
     RC(require_keys(ctx));
     RC(ws_reserve(ctx, aes_scratch(ctx, nblk, 3)));
     WSB(mul, u64, (size_t)nblk * 16 * 3 * ctx->byte_words());
@@ -370,6 +375,7 @@ extern "C" int tfa_aes_round_dev(tfa_ctx *ctx, const uint64_t *rk_round, uint64_
 }
 extern "C" int tfa_add_scalar_dev(tfa_ctx *ctx, uint64_t *states, const uint64_t *ctr_dev, int nblk) {
     Guard g(ctx);
+    if (nblk < 1) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1");
     RC(require_keys(ctx));
     RC(ws_reserve(ctx, add_scalar_scratch(ctx, nblk)));
     return add_scalar_nolock(ctx, states, ctr_dev, nblk);
@@ -398,6 +404,7 @@ static int aes_ctr_nolock(tfa_ctx *ctx, const u64 *rk, const u64 *iv_ct, u64 fir
 }
 extern "C" int tfa_aes_ctr_dev(tfa_ctx *ctx, const uint64_t *rk, const uint64_t *iv_ct, uint64_t first_lo, uint64_t first_hi, int nblk, uint64_t *out) {
     Guard g(ctx);
+    if (nblk < 1) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1");
     RC(require_keys(ctx));
     size_t a = aes_scratch(ctx, nblk, 3), b = add_scalar_scratch(ctx, nblk);
     RC(ws_reserve(ctx, (a > b ? a : b) + (size_t)nblk * 16));
@@ -407,6 +414,7 @@ extern "C" int tfa_aes_ctr_dev(tfa_ctx *ctx, const uint64_t *rk, const uint64_t 
 // ---- host-pointer entry points ---------------------------------------------------------------------
 #define HOST_STATE_CALL(scratch, body)                                                         \
     Guard g(ctx);                                                                              \
+    if (nblk < 1) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1");                        \
     RC(require_keys(ctx));                                                                     \
     const size_t sw = (size_t)nblk * 16 * ctx->byte_words(), rkw = (size_t)11 * 16 * ctx->byte_words(); \
     RC(ws_reserve(ctx, (scratch) + (sw + rkw) * 8));                                           \
@@ -428,6 +436,7 @@ extern "C" int tfa_aes_decryption(tfa_ctx *ctx, const uint64_t *rk, uint64_t *st
 
 extern "C" int tfa_aes_round(tfa_ctx *ctx, const uint64_t *round_key, uint64_t *states, int nblk) {
     Guard g(ctx);
+    if (nblk < 1) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1");
     RC(require_keys(ctx));
     const size_t bw = ctx->byte_words(), sw = (size_t)nblk * 16 * bw;
     RC(ws_reserve(ctx, aes_scratch(ctx, nblk, 3) + (sw + 16 * bw) * 8));
@@ -454,6 +463,7 @@ extern "C" int tfa_aes_key_expansion(tfa_ctx *ctx, const uint64_t *key_ct, const
 }
 extern "C" int tfa_add_scalar(tfa_ctx *ctx, uint64_t *states, const uint64_t *counters, int nblk) {
     Guard g(ctx);
+    if (nblk < 1) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1");
     RC(require_keys(ctx));
     const size_t sw = (size_t)nblk * 16 * ctx->byte_words();
     RC(ws_reserve(ctx, add_scalar_scratch(ctx, nblk) + sw * 8 + (size_t)nblk * 16));
@@ -466,6 +476,7 @@ extern "C" int tfa_add_scalar(tfa_ctx *ctx, uint64_t *states, const uint64_t *co
 }
 extern "C" int tfa_aes_ctr(tfa_ctx *ctx, const uint64_t *round_keys, const uint64_t *iv_ct, uint64_t first_lo, uint64_t first_hi, int nblk, uint64_t *out) {
     Guard g(ctx);
+    if (nblk < 1) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1");
     RC(require_keys(ctx));
     const size_t bw = ctx->byte_words(), sw = (size_t)nblk * 16 * bw, rkw = 176 * bw;
     size_t a = aes_scratch(ctx, nblk, 3), b = add_scalar_scratch(ctx, nblk);
@@ -480,6 +491,7 @@ extern "C" int tfa_aes_ctr(tfa_ctx *ctx, const uint64_t *round_keys, const uint6
 // linear layers alone
 extern "C" int tfa_add_round_key(tfa_ctx *ctx, uint64_t *states, const uint64_t *round_key, int nblk) {
     Guard g(ctx);
+    if (nblk < 1) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1");
     const size_t bw = ctx->byte_words(), sw = (size_t)nblk * 16 * bw;
     RC(ws_reserve(ctx, (sw + 16 * bw) * 8 + (size_t)nblk * 16 * sizeof(SumEntry)));
     WSB(d_st, u64, sw); WSB(d_rk, u64, 16 * bw);
@@ -491,6 +503,7 @@ extern "C" int tfa_add_round_key(tfa_ctx *ctx, uint64_t *states, const uint64_t 
 }
 extern "C" int tfa_mix_columns(tfa_ctx *ctx, const uint64_t *mul, uint64_t *states_out, int nblk) {
     Guard g(ctx);
+    if (nblk < 1) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1");
     const size_t bw = ctx->byte_words(), sw = (size_t)nblk * 16 * bw;
     RC(ws_reserve(ctx, sw * 4 * 8 + (size_t)nblk * 16 * sizeof(SumEntry)));
     WSB(d_mul, u64, sw * 3); WSB(d_st, u64, sw);
@@ -502,6 +515,7 @@ extern "C" int tfa_mix_columns(tfa_ctx *ctx, const uint64_t *mul, uint64_t *stat
 }
 extern "C" int tfa_inv_mix_columns(tfa_ctx *ctx, const uint64_t *mul, uint64_t *states_out, int nblk) {
     Guard g(ctx);
+    if (nblk < 1) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1");
     const size_t bw = ctx->byte_words(), sw = (size_t)nblk * 16 * bw;
     RC(ws_reserve(ctx, sw * 5 * 8 + (size_t)nblk * 16 * sizeof(SumEntry)));
     WSB(d_mul, u64, sw * 4); WSB(d_st, u64, sw);
@@ -513,6 +527,7 @@ extern "C" int tfa_inv_mix_columns(tfa_ctx *ctx, const uint64_t *mul, uint64_t *
 }
 extern "C" int tfa_shift_rows(tfa_ctx *ctx, uint64_t *states, int nblk, int inverse) {
     Guard g(ctx);
+    if (nblk < 1) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1");
     const size_t bw = ctx->byte_words(), sw = (size_t)nblk * 16 * bw;
     RC(ws_reserve(ctx, sw * 2 * 8 + (size_t)nblk * 16 * sizeof(SumEntry)));
     WSB(d_in, u64, sw); WSB(d_out, u64, sw);
@@ -526,6 +541,7 @@ extern "C" int tfa_shift_rows(tfa_ctx *ctx, uint64_t *states, int nblk, int inve
 // ---- primitives for parity tests ---------------------------------------------------------------------
 extern "C" int tfa_keyswitch(tfa_ctx *ctx, const uint64_t *in, int count, uint64_t *out) {
     Guard g(ctx);
+    if (count < 1) return ctx->fail(TFA_ERR_PARAM, "count must be >= 1");
     RC(require_keys(ctx));
     const size_t iw = (size_t)count * ctx->lw, ow = (size_t)count * (ctx->n + 1);
     RC(ws_reserve(ctx, (iw + ow) * 8 + (size_t)count * ctx->big * ctx->p.ks_level * 2));
@@ -538,6 +554,7 @@ extern "C" int tfa_keyswitch(tfa_ctx *ctx, const uint64_t *in, int count, uint64
 }
 extern "C" int tfa_bootstrap(tfa_ctx *ctx, const uint64_t *in, int count, const uint64_t *lut, uint64_t *out) {
     Guard g(ctx);
+    if (count < 1) return ctx->fail(TFA_ERR_PARAM, "count must be >= 1");
     RC(require_keys(ctx));
     const size_t iw = (size_t)count * (ctx->n + 1), ow = (size_t)count * ctx->lw;
     RC(ws_reserve(ctx, (iw + ow + ctx->N) * 8));
@@ -551,11 +568,13 @@ extern "C" int tfa_bootstrap(tfa_ctx *ctx, const uint64_t *in, int count, const 
 extern "C" int tfa_bootstrap_dev(tfa_ctx *ctx, const uint64_t *in, int count, const uint64_t *lut, uint64_t pre_add_body,
                                  uint64_t post_add_body, uint64_t *out) {
     Guard g(ctx);
+    if (count < 1) return ctx->fail(TFA_ERR_PARAM, "count must be >= 1");
     RC(require_keys(ctx));
     return dev_pbs(ctx, in, count, lut, 1, pre_add_body, post_add_body, out);
 }
 extern "C" int tfa_extract_bits(tfa_ctx *ctx, const uint64_t *in, int count, int delta_log, int nbits, uint64_t *out) {
     Guard g(ctx);
+    if (count < 1) return ctx->fail(TFA_ERR_PARAM, "count must be >= 1");
     RC(require_keys(ctx));
     if (nbits < 1 || delta_log < 1 || delta_log + nbits > 64) return ctx->fail(TFA_ERR_PARAM, "extract_bits: bad delta_log / nbits");
     const int np = ctx->n + 1;
@@ -573,6 +592,7 @@ extern "C" int tfa_extract_bits(tfa_ctx *ctx, const uint64_t *in, int count, int
 }
 extern "C" int tfa_pfks(tfa_ctx *ctx, int key_index, const uint64_t *in, int count, uint64_t *out) {
     Guard g(ctx);
+    if (count < 1) return ctx->fail(TFA_ERR_PARAM, "count must be >= 1");
     RC(require_keys(ctx));
     if (key_index < 0 || key_index > ctx->k) return ctx->fail(TFA_ERR_PARAM, "pfks: bad key index");
     const int kp1 = ctx->k + 1;
@@ -588,6 +608,7 @@ extern "C" int tfa_pfks(tfa_ctx *ctx, int key_index, const uint64_t *in, int cou
 }
 extern "C" int tfa_circuit_bootstrap(tfa_ctx *ctx, const uint64_t *in, int count, uint64_t *ggsw_out) {
     Guard g(ctx);
+    if (count < 1) return ctx->fail(TFA_ERR_PARAM, "count must be >= 1");
     RC(require_keys(ctx));
     const size_t iw = (size_t)count * (ctx->n + 1), ow = (size_t)count * ctx->p.cbs_level * (ctx->k + 1) * ctx->gsz;
     RC(ws_reserve(ctx, (iw + ow + (size_t)count * ctx->lw) * 8 + (size_t)count * (ctx->big + 1) * ctx->p.pfks_level * 2 + (1 << 20)));
@@ -615,6 +636,7 @@ extern "C" int tfa_vertical_packing(tfa_ctx *ctx, const uint64_t *lut, int nouts
 }
 extern "C" int tfa_fourier_forward(tfa_ctx *ctx, const uint64_t *polys, int count, double *out) {
     Guard g(ctx);
+    if (count < 1) return ctx->fail(TFA_ERR_PARAM, "count must be >= 1");
     RC(ws_reserve(ctx, (size_t)count * ctx->N * 8 * 2 + (1 << 20)));
     WSB(d_in, u64, (size_t)count * ctx->N); WSB(d_out, double2, (size_t)count * 256);
     H2D(d_in, polys, (size_t)count * ctx->N);
