@@ -31,9 +31,8 @@ enum { DIFF_ROTATE = 0, DIFF_EXTERNAL = 1 };
 template <int K, int G>
 struct CmuxSmem {
     uint64_t acc[G][K + 1][POLY_N];      // the G accumulators (GLWE, standard domain)
-    cd xb[CMUX_GROUPS][XB_ELEMS];        // exchange / hand-over buffers, one per group
-    cd twf[256];                         // forward mid twiddles [k1][n2]
-    cd twi[256];                         // inverse mid twiddles [n2][k1]
+    cd xb[G * (K + 1)][XB_ELEMS];        // exchange / hand-over buffers, one per busy 16-lane group
+    cd tw[256];                          // mid twiddles, swizzled (fft_core.cuh)
     int rot[G];                          // per-ciphertext rotation amount of the current step, in [0, 2N)
 };
 
@@ -79,6 +78,40 @@ HD int decomp_next(uint32_t &state) {
     return (int)res - (int)(carry << BASE_LOG);
 }
 
+// ---- signed decomposition for (beta, l) = (2^8, 5), the bootstrap-key decomposition (client.rs:42-43) ----
+// All five digits at once: with r = 64 - 40 = 24, x' = x + 2^23 (closest representable) plus the
+// offset 128 * (1 + 2^8 + .. + 2^32) << 24 has, in bits 24..63, the bytes  d_j + 128  of a balanced digit set
+// d_j in [-128, 127] with  sum_j d_j 2^(8j) = closest(x) >> 24  (mod 2^40): adding 128 per byte lets the
+// carries of the signed recoding ripple in ONE 64-bit addition.  XOR with 0x80 per byte then turns
+// d_j + 128 into the two's-complement byte of d_j.  Digit of level 5 (least significant, consumed first) =
+// byte 3 of the low word; the high word holds levels 4, 3, 2, 1 in bytes 0..3.
+// Difference from tfhe-rs' iterator: an exact tie (digit = +-128) is always resolved to -128 (+1 carry)
+// where tfhe-rs picks by a state bit; both recodings represent the same value, so the external product is
+// the same up to the noise realisation.
+#ifndef USE_DECOMP85
+#define USE_DECOMP85 1
+#endif
+#define DECOMP85_ADD 0x8080808080800000ull
+#define DECOMP85_XOR 0x8080808080000000ull
+HD int signed_byte(uint32_t w, int b) {
+#ifdef __CUDA_ARCH__
+    // prmt with sign replication (selector nibble 8|b); __byte_perm() masks that bit off, hence inline PTX
+    int r;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(w), "r"(0x8880 + 0x1111 * b));
+    return r;
+#else
+    return (int)(int8_t)(w >> (8 * b));
+#endif
+}
+// first digit (level 5) and the state word holding the other four
+HD int decomp85_first(uint64_t x, uint32_t &state) {
+    const uint64_t y = (x + DECOMP85_ADD) ^ DECOMP85_XOR;
+    state = (uint32_t)(y >> 32);
+    return signed_byte((uint32_t)y, 3);
+}
+// digit of level lev in 4..1
+HD int decomp85_level(uint32_t state, int lev) { return signed_byte(state, 4 - lev); }
+
 // ---- phase A: build ct1 = (acc * X^rot - acc) [DIFF_ROTATE] or (ext - acc) [DIFF_EXTERNAL] for the
 // 32 coefficients this lane owns, start the decomposition, emit the digits of the first level into v.
 template <int K, int G, int BASE_LOG, int LEVELS, int MODE>
@@ -111,8 +144,14 @@ HD void phase_load_decompose(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg, co
             a0 = e[j] - poly[j];
             a1 = e[j + POLY_M] - poly[j + POLY_M];
         }
-        int d0 = decomp_first<BASE_LOG, LEVELS>(a0, rg.st_re[n1]);
-        int d1 = decomp_first<BASE_LOG, LEVELS>(a1, rg.st_im[n1]);
+        int d0, d1;
+        if (USE_DECOMP85 && BASE_LOG == 8 && LEVELS == 5) {
+            d0 = decomp85_first(a0, rg.st_re[n1]);
+            d1 = decomp85_first(a1, rg.st_im[n1]);
+        } else {
+            d0 = decomp_first<BASE_LOG, LEVELS>(a0, rg.st_re[n1]);
+            d1 = decomp_first<BASE_LOG, LEVELS>(a1, rg.st_im[n1]);
+        }
         rg.v[n1] = cmk((double)d0, (double)d1);
     }
 }
@@ -130,39 +169,46 @@ HD void load_decompose_rot(const uint64_t *poly, int lane, int rot, cd (&v)[16],
         const uint64_t m1 = (uint64_t)0 - (uint64_t)(((s >> 9) ^ (s >> 8)) & 1);
         const uint64_t a0 = ((x0 ^ m0) - m0) - poly[j];
         const uint64_t a1 = ((x1 ^ m1) - m1) - poly[j + POLY_M];
-        const int d0 = decomp_first<BASE_LOG, LEVELS>(a0, st_re[n1]);
-        const int d1 = decomp_first<BASE_LOG, LEVELS>(a1, st_im[n1]);
+        int d0, d1;
+        if (USE_DECOMP85 && BASE_LOG == 8 && LEVELS == 5) {
+            d0 = decomp85_first(a0, st_re[n1]);
+            d1 = decomp85_first(a1, st_im[n1]);
+        } else {
+            d0 = decomp_first<BASE_LOG, LEVELS>(a0, st_re[n1]);
+            d1 = decomp_first<BASE_LOG, LEVELS>(a1, st_im[n1]);
+        }
         v[n1] = cmk((double)d0, (double)d1);
     }
 }
-template <int BASE_LOG>
-HD void next_digits(cd (&v)[16], uint32_t (&st_re)[16], uint32_t (&st_im)[16]) {
+// digits of level lev (LEVELS-1 .. 1; levels are consumed in decreasing order)
+template <int BASE_LOG, int LEVELS>
+HD void next_digits(cd (&v)[16], uint32_t (&st_re)[16], uint32_t (&st_im)[16], int lev) {
 #pragma unroll
     for (int n1 = 0; n1 < 16; n1++) {
-        const int d0 = decomp_next<BASE_LOG>(st_re[n1]);
-        const int d1 = decomp_next<BASE_LOG>(st_im[n1]);
+        int d0, d1;
+        if (USE_DECOMP85 && BASE_LOG == 8 && LEVELS == 5) {
+            d0 = decomp85_level(st_re[n1], lev);
+            d1 = decomp85_level(st_im[n1], lev);
+        } else {
+            d0 = decomp_next<BASE_LOG>(st_re[n1]);
+            d1 = decomp_next<BASE_LOG>(st_im[n1]);
+        }
         v[n1] = cmk((double)d0, (double)d1);
     }
 }
-// digits of the next level (level index decreasing)
-template <int K, int G, int BASE_LOG>
-HD void phase_next_digits(int tid, CmuxRegs<K, G> &rg) {
+template <int K, int G, int BASE_LOG, int LEVELS>
+HD void phase_next_digits(int tid, CmuxRegs<K, G> &rg, int lev) {
     if ((tid >> 4) >= G * (K + 1)) return;
-#pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) {
-        int d0 = decomp_next<BASE_LOG>(rg.st_re[n1]);
-        int d1 = decomp_next<BASE_LOG>(rg.st_im[n1]);
-        rg.v[n1] = cmk((double)d0, (double)d1);
-    }
+    next_digits<BASE_LOG, LEVELS>(rg.v, rg.st_re, rg.st_im, lev);
 }
 // ---- forward FFT of the digit polynomial held in v -------------------------------------------
 // The *_b variants take the base of a [16][XB_ELEMS] exchange / hand-over buffer and the twiddle table
 // explicitly (the warp-specialised PBS kernel double-buffers it); the CmuxSmem forms use sm.xb.
 template <int K, int G>
-HD void phase_fwd1_b(int tid, cd (*xb)[XB_ELEMS], const cd *twf, cd (&v)[16]) {
+HD void phase_fwd1_b(int tid, cd (*xb)[XB_ELEMS], const cd *tw, cd (&v)[16]) {
     const int gid = tid >> 4, lane = tid & 15;
     if (gid >= G * (K + 1)) return;
-    fft256_fwd_pass1(v, lane, twf, xb[gid]);
+    fft256_fwd_pass1(v, lane, tw, xb[gid]);
 }
 template <int K, int G>
 HD void phase_fwd2_b(int tid, cd (*xb)[XB_ELEMS], cd (&v)[16]) {
@@ -178,7 +224,7 @@ HD void phase_fwd3_b(int tid, cd (*xb)[XB_ELEMS], cd (&v)[16]) {
     for (int k2 = 0; k2 < 16; k2++) xb[gid][lane + 16 * k2] = v[rev4(k2)];
 }
 template <int K, int G>
-HD void phase_fwd1(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) { phase_fwd1_b<K, G>(tid, sm.xb, sm.twf, rg.v); }
+HD void phase_fwd1(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) { phase_fwd1_b<K, G>(tid, sm.xb, sm.tw, rg.v); }
 template <int K, int G>
 HD void phase_fwd2(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) { phase_fwd2_b<K, G>(tid, sm.xb, rg.v); }
 template <int K, int G>
@@ -257,10 +303,10 @@ HD void phase_inv1_b(int tid, cd (*xb)[XB_ELEMS], cd (&v)[16]) {
     fft256_inv_pass1_compute(v);
 }
 template <int K, int G>
-HD void phase_inv2_b(int tid, cd (*xb)[XB_ELEMS], const cd *twi, cd (&v)[16]) {
+HD void phase_inv2_b(int tid, cd (*xb)[XB_ELEMS], const cd *tw, cd (&v)[16]) {
     const int gid = tid >> 4, lane = tid & 15;
     if (gid >= G * (K + 1)) return;
-    fft256_inv_pass1_store(v, lane, twi, xb[gid]);
+    fft256_inv_pass1_store(v, lane, tw, xb[gid]);
 }
 // acc: base of the [G][K+1][512] accumulator array
 template <int K, int G>
@@ -280,7 +326,7 @@ HD void phase_inv3_b(int tid, cd (*xb)[XB_ELEMS], uint64_t (*acc)[K + 1][POLY_N]
 template <int K, int G>
 HD void phase_inv1(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) { phase_inv1_b<K, G>(tid, sm.xb, rg.v); }
 template <int K, int G>
-HD void phase_inv2(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) { phase_inv2_b<K, G>(tid, sm.xb, sm.twi, rg.v); }
+HD void phase_inv2(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) { phase_inv2_b<K, G>(tid, sm.xb, sm.tw, rg.v); }
 template <int K, int G>
 HD void phase_inv3(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg) { phase_inv3_b<K, G>(tid, sm.xb, sm.acc, rg.v); }
 

@@ -11,10 +11,7 @@ struct EmuCta {
     CmuxSmem<K, G> sm;
     std::vector<CmuxRegs<K, G>> rg;
     EmuCta() : rg(CMUX_THREADS) {
-        cd tw[512];
-        make_twiddle_tables(tw);
-        memcpy(sm.twf, tw, sizeof(sm.twf));
-        memcpy(sm.twi, tw + 256, sizeof(sm.twi));
+        make_twiddle_table(sm.tw);
         memset(sm.acc, 0, sizeof(sm.acc));
         for (int g = 0; g < G; g++) sm.rot[g] = 0;
     }
@@ -23,7 +20,7 @@ struct EmuCta {
     void cmux_step(const cd *ggsw, const uint64_t *const *ext) {
         ALL((phase_load_decompose<K, G, BASE_LOG, LEVELS, MODE>(tid, sm, rg[tid], ext)));
         for (int lev = LEVELS; lev >= 1; lev--) {
-            if (lev != LEVELS) ALL((phase_next_digits<K, G, BASE_LOG>(tid, rg[tid])));
+            if (lev != LEVELS) ALL((phase_next_digits<K, G, BASE_LOG, LEVELS>(tid, rg[tid], lev)));
             ALL((phase_fwd1<K, G>(tid, sm, rg[tid])));
             ALL((phase_fwd2<K, G>(tid, sm, rg[tid])));
             ALL((phase_fwd3<K, G>(tid, sm, rg[tid])));
@@ -38,9 +35,9 @@ struct EmuCta {
 
 // forward transform of one torus / integer polynomial through the group code path (group 0)
 static void emu_forward(const uint64_t *poly, cd *out) {
-    static cd tw[512];
+    static cd tw[256];
     static bool init = false;
-    if (!init) { make_twiddle_tables(tw); init = true; }
+    if (!init) { make_twiddle_table(tw); init = true; }
     cd xb[XB_ELEMS];
     cd v[16][16];
     for (int lane = 0; lane < 16; lane++) { load_torus_poly(v[lane], lane, poly); fft256_fwd_pass1(v[lane], lane, tw, xb); }

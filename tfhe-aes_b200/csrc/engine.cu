@@ -91,8 +91,8 @@ extern "C" int tfa_ctx_create(const tfa_params *p, int device, void *stream, tfa
         e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return TFA_ERR_CUDA; }
     }
-    cd tw[512];
-    make_twiddle_tables(tw);
+    cd tw[256];
+    make_twiddle_table(tw);
     e = cudaMalloc(&ctx->tw, sizeof(tw));
     if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->tw, tw, sizeof(tw), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -259,6 +259,27 @@ int dev_pbs(tfa_ctx *ctx, const u64 *in, int count, const u64 *lut, u64 in_scale
     // ciphertexts per CTA the phase-synchronous kernel wins (13.9 vs 15.8 ms at G = 3: its single hand-over
     // buffer makes the two roles wait for each other, and a second buffer does not fit in shared memory).
     const int G = pick_G(ctx->k, count);
+    static const int stagger = getenv("TFA_PBS_STAGGER") ? atoi(getenv("TFA_PBS_STAGGER")) : 0;
+    a.stagger = stagger;
+    static const bool timing = getenv("TFA_PBS_TIMING") != nullptr;
+    if (timing && G == 3 && ctx->k == 4) {
+        // debug aid: per-phase clock64() totals of thread 0 of block 0, printed to stderr
+        uint64_t *d = nullptr, h[16] = {0};
+        CU(cudaMalloc(&d, sizeof(h)));
+        a.dbg = d;
+        CU(launch_pbs(ctx->k, G, ctx->p.pbs_base_log, ctx->p.pbs_level, a, ctx->stream));
+        CU(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d);
+        static const char *nm[9] = {"decompose", "fwd_fft", "bar_after_fwd", "wait_full", "mac", "bar_after_mac", "inv0+bar", "inv_fft", "bar_end"};
+        uint64_t tot = 0;
+        for (int k = 0; k < 9; k++) tot += h[k];
+        fprintf(stderr, "[pbs timing] cycles per CMux step (thread 0, block 0), total %.0f:", (double)tot / ctx->n);
+        for (int k = 0; k < 9; k++) fprintf(stderr, " %s=%.0f", nm[k], (double)h[k] / ctx->n);
+        fprintf(stderr, "\n");
+        ctx->launches++;
+        return TFA_OK;
+    }
     if (G == 1) CU(launch_pbs_ws(ctx->k, G, ctx->p.pbs_base_log, ctx->p.pbs_level, a, ctx->stream));
     else CU(launch_pbs(ctx->k, G, ctx->p.pbs_base_log, ctx->p.pbs_level, a, ctx->stream));
     ctx->launches++;

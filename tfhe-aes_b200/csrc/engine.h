@@ -25,7 +25,7 @@ struct tfa_ctx {
     uint8_t *kp_pfpksk;    // PFPKSK list, same layout [k+1][ntiles][kchunks][2048]
     u64 *ksk;              // standard-domain staging, only alive during key preparation: [big*ks_level][ks_cols_pad]
     u64 *pfpksk;           //   [k+1][(big+1)*pfks_level][gsz]
-    double2 *tw;           // 512 twiddles
+    double2 *tw;           // 256 mid twiddles (twiddle_host.h)
     int ks_cols_pad;
     bool keys_allocated, keys_ready;
 

@@ -8,7 +8,7 @@
 // Decomposition ("four-step", 16 x 16): n = 16 n1 + n2, k = k1 + 16 k2.
 //   pass 1 (lane n2):  T[k1] = sum_n1 z[16 n1 + n2] phi^(n1) W16^(n1 k1),  phi = exp(2 pi i/64)
 //   mid twiddle:       T[k1] *= theta^(n2 (4 k1 + 1))
-//   exchange through shared memory (16 x 16 transpose inside one half-warp)
+//   exchange through shared memory (16 x 16 transpose inside one half-warp, XOR-swizzled, no padding)
 //   pass 2 (lane k1):  X[k1 + 16 k2] = sum_n2 T[k1][n2] W16^(n2 k2)
 // Each of the 16 lanes holds 16 complex values in registers, so a transform costs one shared-memory
 // round trip.  Everything here is __host__ __device__ so the CPU emulation in emu.cu runs the very
@@ -76,51 +76,45 @@ HD void fft16(cd (&v)[16]) {
     for (int k1 = 0; k1 < 4; k1++) radix4<SIGN>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
 }
 
-// Exchange buffer of one 16-lane group: 16 rows of 17 complex (one pad element per row keeps the
-// transposed reads at two wavefronts per half-warp).  The same storage, read linearly as 256
-// complex, is also the hand-over format to / from the multiply-accumulate phase.
-#define XB_STRIDE 17
-#define XB_ELEMS (16 * XB_STRIDE)
+// a * conj(b)
+HD cd cmul_conj(cd a, cd b) { return cmk(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
 
-// Mid-twiddle tables (filled once per CTA): twf[k1*16 + n2] = theta^(n2 (4 k1 + 1)),
-// twi[n2*16 + k1] = conj of the same value.
-HD void fft256_fwd_pass1(cd (&v)[16], int lane, const cd *twf, cd *xb) {
+// Exchange buffer of one 16-lane group: a 16 x 16 matrix of complex values WITHOUT padding, element
+// (row, col) stored at row*16 + (col ^ row).  Writing a fixed row from 16 lanes (col = lane) touches the 256
+// contiguous bytes of that row; reading a fixed column from 16 lanes (row = lane) touches every 16-byte bank
+// group exactly twice: both directions cost the minimum of two 128-byte wavefronts per half-warp.  The same
+// storage, read linearly as 256 complex, is also the hand-over format to / from the multiply-accumulate phase.
+#define XB_ELEMS 256
+HD constexpr int xb_idx(int row, int col) { return row * 16 + (col ^ row); }
+
+// Mid-twiddle table (filled once per CTA, make_twiddle_table): tw[xb_idx(k1, n2)] = theta^(n2 (4 k1 + 1)).
+// The forward pass reads it along rows (k1 fixed, lane = n2), the inverse pass along columns (n2 fixed,
+// lane = k1) and conjugates; the swizzle keeps both conflict-free, so one 4 KB table serves both.
+HD void fft256_fwd_pass1(cd (&v)[16], int lane, const cd *tw, cd *xb) {
 #pragma unroll
     for (int n1 = 1; n1 < 16; n1++) v[n1] = mul_w64<1>(v[n1], n1);
     fft16<1>(v);
 #pragma unroll
-    for (int k1 = 0; k1 < 16; k1++) xb[k1 * XB_STRIDE + lane] = cmul(v[rev4(k1)], twf[k1 * 16 + lane]);
-}
-// the same in two halves, so that the arithmetic can be scheduled before the exchange buffer is free
-HD void fft256_fwd_pass1_compute(cd (&v)[16], int lane, const cd *twf) {
-#pragma unroll
-    for (int n1 = 1; n1 < 16; n1++) v[n1] = mul_w64<1>(v[n1], n1);
-    fft16<1>(v);
-#pragma unroll
-    for (int k1 = 0; k1 < 16; k1++) v[rev4(k1)] = cmul(v[rev4(k1)], twf[k1 * 16 + lane]);
-}
-HD void fft256_fwd_pass1_store(const cd (&v)[16], int lane, cd *xb) {
-#pragma unroll
-    for (int k1 = 0; k1 < 16; k1++) xb[k1 * XB_STRIDE + lane] = v[rev4(k1)];
+    for (int k1 = 0; k1 < 16; k1++) xb[xb_idx(k1, lane)] = cmul(v[rev4(k1)], tw[xb_idx(k1, lane)]);
 }
 // lane = k1.  Out: X[lane + 16 k2] at v[rev4(k2)]
 HD void fft256_fwd_pass2(cd (&v)[16], int lane, const cd *xb) {
 #pragma unroll
-    for (int n2 = 0; n2 < 16; n2++) v[n2] = xb[lane * XB_STRIDE + n2];
+    for (int n2 = 0; n2 < 16; n2++) v[n2] = xb[xb_idx(lane, n2)];
     fft16<1>(v);
 }
-// lane = k1.  In: v[k2] = X[lane + 16 k2].  Writes twiddled U[n2] to xb[n2][lane].
+// lane = k1.  In: v[k2] = X[lane + 16 k2].  Writes twiddled U[n2] to element (n2, lane).
 HD void fft256_inv_pass1_compute(cd (&v)[16]) { fft16<-1>(v); }
-HD void fft256_inv_pass1_store(cd (&v)[16], int lane, const cd *twi, cd *xb) {
+HD void fft256_inv_pass1_store(cd (&v)[16], int lane, const cd *tw, cd *xb) {
 #pragma unroll
-    for (int n2 = 0; n2 < 16; n2++) xb[n2 * XB_STRIDE + lane] = cmul(v[rev4(n2)], twi[n2 * 16 + lane]);
+    for (int n2 = 0; n2 < 16; n2++) xb[xb_idx(n2, lane)] = cmul_conj(v[rev4(n2)], tw[xb_idx(lane, n2)]);
 }
 // lane = n2.  Out: z[16 n1 + lane] * 256 at v[rev4(n1)] before the final untwist; this applies the
 // untwist conj(phi^n1) and the 1/256 scale and returns natural order in v[n1].
 HD void fft256_inv_pass2(cd (&v)[16], int lane, const cd *xb) {
     cd t[16];
 #pragma unroll
-    for (int k1 = 0; k1 < 16; k1++) t[k1] = xb[lane * XB_STRIDE + k1];
+    for (int k1 = 0; k1 < 16; k1++) t[k1] = xb[xb_idx(lane, k1)];
     fft16<-1>(t);
 #pragma unroll
     for (int n1 = 0; n1 < 16; n1++) {
@@ -129,18 +123,30 @@ HD void fft256_inv_pass2(cd (&v)[16], int lane, const cd *xb) {
     }
 }
 
-// round-to-nearest f64 -> u64 modulo 2^64 (SURVEY §9.6 "round to nearest, reduce mod 2^64")
+// round-to-nearest(-even) f64 -> u64 modulo 2^64 (SURVEY §9.6 "round to nearest, reduce mod 2^64"), valid for
+// |v| < 2^115 (the level-1 products of vertical packing reach ~2^83, worst case 2^89).  No conversion
+// instructions (FRND / F2I issue at 1/4 of the FP64 rate on B200, scratch/mb_xu.cu): with M = 1.5 * 2^52,
+//   q = v * 2^-64 + M,  w = v - (q - M) * 2^64     -> exact, |w| <= 2^63, w = v (mod 2^64)
+//   t = w * 2^-32 + M                              -> low word of t = h mod 2^32,  h = rint(w / 2^32)
+//   r = w - h * 2^32                               -> exact, |r| <= 2^31
+//   u = r + M                                      -> bits(u) - bits(M) = rint(r) as a signed 64-bit integer
+//   result = (h << 32) + rint(r) = rint(v)  (mod 2^64)
 HD uint64_t f64_to_torus(double v) {
-    double q = v * (1.0 / 18446744073709551616.0);
+    const double M = 6755399441055744.0;
+    const double q = fma(v, 1.0 / 18446744073709551616.0, M);
+    const double w = fma(-(q - M), 18446744073709551616.0, v);
+    const double t = fma(w, 1.0 / 4294967296.0, M);
+    const double h = t - M;
+    const double r = fma(-h, 4294967296.0, w);
+    const double u = r + M;
 #ifdef __CUDA_ARCH__
-    double r = fma(-18446744073709551616.0, rint(q), v);
-    double rr = rint(r);
-    if (rr >= 9223372036854775808.0) rr -= 18446744073709551616.0;
-    return (uint64_t)__double2ll_rn(rr);
+    const uint32_t lo = (uint32_t)__double2loint(u);
+    const uint32_t hi = (uint32_t)__double2loint(t) + (uint32_t)__double2hiint(u) - 0x43380000u;
+    return ((uint64_t)hi << 32) | lo;
 #else
-    double r = v - 18446744073709551616.0 * __builtin_nearbyint(q);
-    double rr = __builtin_nearbyint(r);
-    if (rr >= 9223372036854775808.0) rr -= 18446744073709551616.0;
-    return (uint64_t)(int64_t)rr;
+    uint64_t bt, bu;
+    __builtin_memcpy(&bt, &t, 8);
+    __builtin_memcpy(&bu, &u, 8);
+    return (bt << 32) + (bu - 0x4338000000000000ull);
 #endif
 }

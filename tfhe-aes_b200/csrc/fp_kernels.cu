@@ -16,8 +16,7 @@ __device__ __forceinline__ CmuxSmem<K, G> &smem_view(unsigned char *raw) {
 
 template <int K, int G>
 __device__ __forceinline__ void load_twiddles(CmuxSmem<K, G> &sm, const cd *tw, int tid) {
-    cd *dst = sm.twf;  // twf and twi are contiguous
-    for (int i = tid; i < 512; i += CMUX_THREADS) dst[i] = tw[i];
+    for (int i = tid; i < 256; i += CMUX_THREADS) sm.tw[i] = tw[i];
 }
 
 // One full CMux step on the resident accumulators (all barriers included).
@@ -27,7 +26,7 @@ __device__ __forceinline__ void cmux_step(int tid, CmuxSmem<K, G> &sm, CmuxRegs<
     phase_load_decompose<K, G, BASE_LOG, LEVELS, MODE>(tid, sm, rg, ext);
 #pragma unroll 1
     for (int lev = LEVELS; lev >= 1; lev--) {
-        if (lev != LEVELS) phase_next_digits<K, G, BASE_LOG>(tid, rg);
+        if (lev != LEVELS) phase_next_digits<K, G, BASE_LOG, LEVELS>(tid, rg, lev);
         phase_fwd1<K, G>(tid, sm, rg);
         __syncwarp();
         phase_fwd2<K, G>(tid, sm, rg);
@@ -60,85 +59,128 @@ __device__ __forceinline__ void sample_extract(int tid, const CmuxSmem<K, G> &sm
 // ------------------------------------------------------------------------------------------------
 // PBS: out[ct] = SampleExtract( BlindRotate(lut * X^-b~, a~, BSK) ) + post_add on the body
 //
-// Bootstrap-key streaming: the Fourier BSK slice of one CMux step is 25 rows x 20 KB (K=4).  Every
-// thread owns Fourier point p = tid and needs, per row, the K+1 complex values [row][0..K][p]
-// (each cp.async instruction of a warp moves 512 contiguous bytes).
-// Those are prefetched with cp.async.cg (L2 -> shared memory, no register staging) into a ring of
-// BSK_RING row-slots, thread-private (each thread only reads what it copied itself, so
-// cp.async.wait_group is the only synchronisation), BSK_RING rows ahead of the multiply-accumulate
-// that consumes them — across level and iteration boundaries, so the L2 latency is hidden behind the
-// FFT phases.  All CTAs walk the key in the same order, so the slice is an L2 hit for all but the first.
+// Bootstrap-key streaming: the Fourier BSK slice of one CMux step is LEVELS x (K+1) rows of (K+1) x 4 KB
+// (K=4: 25 rows x 20 KB), stored in consumption order, each row [col][p] contiguous.  Rows are streamed
+// L2 -> shared memory by the TMA engine (cp.async.bulk, one copy per row issued by ONE lane) into a ring that
+// holds exactly one level (K+1 slots).  One FULL mbarrier counts the K+1 rows of a level (arrive.expect_tx per
+// row + transaction bytes); every thread waits on it ONCE per level, before the multiply-accumulate phase, and
+// then runs the K+1 rows back to back.  Slots are handed back row by row: each warp arrives on the slot's
+// EMPTY mbarrier after its multiply-accumulate of the row, and one lane (the role rotates over the warps)
+// refills the slot freed one row earlier with the same row of the next level; the last slot of a level is
+// refilled right after the CTA barrier that ends the phase.  So the key for level l+1 is requested while level
+// l is being consumed and lands during the FFT phase in between; no thread spends issue slots or LSU
+// wavefronts on the copy (the per-thread cp.async ring of the first build cost 8 % of all instructions and
+// 37 % of the shared-memory wavefronts of the kernel, profiles/r1_pbs_source_phases.txt).  All CTAs walk the
+// key in the same order, so HBM sees the key once per wave and L2 serves the other CTAs.
 // ------------------------------------------------------------------------------------------------
-#define BSK_RING 4
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one bulk copy global -> shared (TMA engine), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
-template <int K, int G, int BASE_LOG, int LEVELS>
+template <int K, int G>
+struct PbsSmemLayout {
+    static constexpr size_t ROW_ELEMS = (size_t)POLY_M * (K + 1);
+    static constexpr size_t ring_off = (sizeof(CmuxSmem<K, G>) + 127) & ~(size_t)127;
+    static constexpr size_t bar_off = ring_off + (K + 1) * ROW_ELEMS * sizeof(cd);   // FULL, EMPTY[K+1]
+    static constexpr size_t bytes = bar_off + (K + 2) * sizeof(uint64_t);
+};
+
+// modulus switch to 2N: a~ = (a * in_scale [+ pre_add on the body] + 2^53) >> 54
+__device__ __forceinline__ int mod_switch_2n(const PbsArgs &a, int ct, int i) {
+    uint64_t x = a.lwe_in[(size_t)ct * (a.lwe_dim + 1) + i] * a.in_scale;
+    if (i == a.lwe_dim) x += a.pre_add_body;
+    return (int)((x + (1ull << 53)) >> 54) & (2 * POLY_N - 1);
+}
+
+// TIMING = true (debug builds of the launcher only, PbsArgs::dbg != nullptr): thread 0 accumulates clock64() deltas per
+// phase in shared memory and block 0 writes them to dbg[0..PT_COUNT).
+enum { PT_DECOMP, PT_FWD, PT_BAR_FWD, PT_WAIT_FULL, PT_MAC, PT_BAR_MAC, PT_INV0, PT_INV, PT_BAR_END, PT_COUNT };
+template <int K, int G, int BASE_LOG, int LEVELS, bool TIMING = false>
 __global__ void __launch_bounds__(CMUX_THREADS, 1) pbs_kernel(PbsArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ long long tacc[PT_COUNT];
+    long long tlast = 0;
+#define PT(k) do { if (TIMING && threadIdx.x == 0) { const long long t_ = clock64(); tacc[k] += t_ - tlast; tlast = t_; } } while (0)
+    typedef PbsSmemLayout<K, G> L;
     CmuxSmem<K, G> &sm = smem_view<K, G>(smem_raw);
-    cd *ring = reinterpret_cast<cd *>(smem_raw + sizeof(CmuxSmem<K, G>));            // [BSK_RING][256][K+1]
-    uint16_t *ahat = reinterpret_cast<uint16_t *>(ring + BSK_RING * POLY_M * (K + 1));
-    CmuxRegs<K, G> rg;
-    const int tid = threadIdx.x;
-    const int n = a.lwe_dim, np = a.lwe_dim + 1;
-    const int ct0 = blockIdx.x * G;
+    constexpr int RING = K + 1;                          // one level of the GGSW
     constexpr int ROWS = LEVELS * (K + 1);               // GGSW rows per CMux step, stored in consumption order
-    constexpr size_t ROW_ELEMS = (size_t)POLY_M * (K + 1);
+    constexpr int ROW_ELEMS = (int)L::ROW_ELEMS;
     constexpr unsigned ROW_BYTES = (unsigned)(ROW_ELEMS * sizeof(cd));
-    constexpr unsigned RING_BYTES = BSK_RING * ROW_BYTES;
-    // prefetch head: the key is walked linearly, one row (K+1 polynomials of 256 points) at a time
-    const cd *pf_src = a.bsk + tid;
-    long pf_left = (long)n * ROWS;
-    const unsigned ring_u32 = (unsigned)__cvta_generic_to_shared(ring) + tid * (unsigned)sizeof(cd);
-    unsigned pf_off = 0;
-    auto issue = [&]() {
-        if (pf_left > 0) {
-#pragma unroll
-            for (int c = 0; c <= K; c++)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(ring_u32 + pf_off + c * (POLY_M * (unsigned)sizeof(cd))),
-                             "l"(pf_src + c * POLY_M));
-            pf_src += ROW_ELEMS;
-            pf_left--;
-            pf_off += ROW_BYTES;
-            if (pf_off == RING_BYTES) pf_off = 0;
-        }
-        cp_async_commit();                               // always commit: keeps the group count uniform
+    cd *ring = reinterpret_cast<cd *>(smem_raw + L::ring_off);                 // [RING][K+1][256]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + L::bar_off);      // one per level
+    uint64_t *empty = full + 1;                                                // [RING]
+    CmuxRegs<K, G> rg;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = a.lwe_dim;
+    const int ct0 = blockIdx.x * G;
+    const int nrows = n * ROWS;
+    // fetch row q into slot q % RING (the caller knows the slot is free)
+    auto produce = [&](int q) {
+        const int slot = q % RING;
+        mbar_arrive_expect_tx(full, ROW_BYTES);
+        bulk_copy_g2s(ring + (size_t)slot * ROW_ELEMS, a.bsk + (size_t)q * ROW_ELEMS, ROW_BYTES, full);
     };
-#pragma unroll
-    for (int s = 0; s < BSK_RING; s++) issue();
-
-    load_twiddles<K, G>(sm, a.tw, tid);
-    // modulus switch to 2N: a~ = (a + 2^53) >> 54
-    for (int idx = tid; idx < G * np; idx += CMUX_THREADS) {
-        const int g = idx / np, i = idx % np;
-        const int ct = min(ct0 + g, a.count - 1);
-        uint64_t x = a.lwe_in[(size_t)ct * np + i] * a.in_scale;
-        if (i == n) x += a.pre_add_body;
-        ahat[g * np + i] = (uint16_t)((x + (1ull << 53)) >> 54);
+    if (tid == 0) {
+        mbar_init(full, RING);
+        for (int s = 0; s < RING; s++) mbar_init(&empty[s], CMUX_THREADS / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (tid == 0)
+        for (int q = 0; q < RING; q++) produce(q);       // nrows >= RING always (n >= 1, LEVELS >= 1)
+
+    load_twiddles<K, G>(sm, a.tw, tid);
     for (int g = 0; g < G; g++) {
-        const int bhat = ahat[g * np + n];
+        const int bhat = mod_switch_2n(a, min(ct0 + g, a.count - 1), n);
         const int rot = (2 * POLY_N - bhat) & (2 * POLY_N - 1);
         for (int idx = tid; idx < (K + 1) * POLY_N; idx += CMUX_THREADS) {
             const int r = idx / POLY_N, j = idx % POLY_N;
             sm.acc[g][r][j] = (r == K) ? rotated_coef(a.lut, j, rot) : 0;
         }
     }
-    if (tid < G) sm.rot[tid] = ahat[tid * np];
+    // thread g < G tracks the rotation of ciphertext g: the mask element of the NEXT step is loaded from global
+    // memory one step ahead, so its latency hides behind a whole CMux
+    const int my_ct = min(ct0 + min(tid, G - 1), a.count - 1);
+    int next_rot = 0;
+    if (tid < G) sm.rot[tid] = mod_switch_2n(a, my_ct, 0);
+    if (a.stagger > 0 && (blockIdx.x & 1)) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < a.stagger) {}
+    }
+    if (TIMING && tid == 0) { for (int k = 0; k < PT_COUNT; k++) tacc[k] = 0; tlast = clock64(); }
     __syncthreads();
-    unsigned rd_off = 0;                                 // ring offset of the next row to consume
+    int q = 0;                                           // next row to consume (uniform over the CTA)
+    unsigned level_parity = 0;
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
         // a step whose rotations are all zero adds exactly zero (ct1 == 0): it is executed like any
-        // other so that the key walk stays in lock-step with the prefetch ring
+        // other so that the key walk stays in lock-step with the ring
+        if (tid < G && i + 1 < n) next_rot = mod_switch_2n(a, my_ct, i + 1);
         phase_load_decompose<K, G, BASE_LOG, LEVELS, DIFF_ROTATE>(tid, sm, rg, nullptr);
+        PT(PT_DECOMP);
 #pragma unroll 1
         for (int lev = LEVELS; lev >= 1; lev--) {
             phase_fwd1<K, G>(tid, sm, rg);
@@ -146,31 +188,51 @@ __global__ void __launch_bounds__(CMUX_THREADS, 1) pbs_kernel(PbsArgs a) {
             phase_fwd2<K, G>(tid, sm, rg);
             __syncwarp();
             phase_fwd3<K, G>(tid, sm, rg);
+            PT(PT_FWD);
             __syncthreads();
+            PT(PT_BAR_FWD);
+            mbar_wait(full, level_parity);               // the K+1 rows of this level have landed
+            level_parity ^= 1;
+            PT(PT_WAIT_FULL);
 #pragma unroll
-            for (int r = 0; r <= K; r++) {
-                cp_async_wait<BSK_RING - 1>();
-                phase_mac_row<K, G>(tid, sm, rg, r, reinterpret_cast<const cd *>(reinterpret_cast<const unsigned char *>(ring) + rd_off) + tid);
-                rd_off += ROW_BYTES;
-                if (rd_off == RING_BYTES) rd_off = 0;
-                issue();
+            for (int r = 0; r <= K; r++, q++) {
+                phase_mac_row<K, G>(tid, sm, rg, r, ring + (size_t)r * ROW_ELEMS + tid);
+                __syncwarp();
+                if (lane == 0) {
+                    // the warp's reads of slot r are complete (their values fed the FMAs above)
+                    if (r < K) mbar_arrive(&empty[r]);
+                    // refill the slot freed one row earlier, once every warp has released it
+                    if (r >= 1 && warp == (q & (CMUX_THREADS / 32 - 1)) && q - 1 + RING < nrows) {
+                        mbar_wait(&empty[r - 1], (level_parity ^ 1) & 1);
+                        produce(q - 1 + RING);
+                    }
+                }
                 // the digits of the next level (integer + conversion pipes) are extracted in the shadow of the
                 // multiply-accumulate (FP64 pipe): v is free during this phase
-                if (r == 0 && lev > 1) phase_next_digits<K, G, BASE_LOG>(tid, rg);
+                if (r == 0 && lev > 1) phase_next_digits<K, G, BASE_LOG, LEVELS>(tid, rg, lev - 1);
             }
+            PT(PT_MAC);
             __syncthreads();
+            // every warp is past the phase: the last slot is free
+            if (tid == 0 && q - 1 + RING < nrows) produce(q - 1 + RING);
+            PT(PT_BAR_MAC);
         }
         phase_inv0<K, G>(tid, sm, rg);
         __syncthreads();
+        PT(PT_INV0);
         phase_inv1<K, G>(tid, sm, rg);
         __syncwarp();
         phase_inv2<K, G>(tid, sm, rg);
         __syncwarp();
         phase_inv3<K, G>(tid, sm, rg);
-        if (tid < G && i + 1 < n) sm.rot[tid] = ahat[tid * np + i + 1];
+        if (tid < G) sm.rot[tid] = next_rot;
+        PT(PT_INV);
         __syncthreads();
+        PT(PT_BAR_END);
     }
-    cp_async_wait<0>();
+    if (TIMING && tid == 0 && blockIdx.x == 0)
+        for (int k = 0; k < PT_COUNT; k++) a.dbg[k] = (uint64_t)tacc[k];
+#undef PT
     for (int g = 0; g < G; g++)
         if (ct0 + g < a.count) sample_extract<K, G>(tid, sm, g, a.out + (size_t)(ct0 + g) * (K * POLY_N + 1), a.post_add);
 }
@@ -252,7 +314,7 @@ __global__ void __launch_bounds__(CMUX_THREADS, 2) fourier_convert_kernel(Conver
     cd *xb_all = reinterpret_cast<cd *>(smem_raw);
     cd *tw = xb_all + CMUX_GROUPS * XB_ELEMS;
     const int tid = threadIdx.x, gid = tid >> 4, lane = tid & 15;
-    for (int i = tid; i < 512; i += CMUX_THREADS) tw[i] = a.tw[i];
+    for (int i = tid; i < 256; i += CMUX_THREADS) tw[i] = a.tw[i];
     __syncthreads();
     const long q = (long)blockIdx.x * CMUX_GROUPS + gid;
     const bool active = q < a.npoly;
@@ -285,14 +347,20 @@ static cudaError_t set_smem(F f, size_t bytes) {
 
 #define LAUNCH_PBS(k, g, bl, lv)                                                               \
     if (K == k && G == g && base_log == bl && levels == lv) {                                  \
-        size_t smem = sizeof(CmuxSmem<k, g>) + (size_t)BSK_RING * POLY_M * (k + 1) * sizeof(cd) + \
-                      (size_t)g * (a.lwe_dim + 1) * sizeof(uint16_t);                            \
+        const size_t smem = PbsSmemLayout<k, g>::bytes;                                        \
         cudaError_t e = set_smem(pbs_kernel<k, g, bl, lv>, smem);                              \
         if (e != cudaSuccess) return e;                                                        \
         pbs_kernel<k, g, bl, lv><<<(a.count + g - 1) / g, CMUX_THREADS, smem, s>>>(a);         \
         return cudaGetLastError();                                                             \
     }
 cudaError_t launch_pbs(int K, int G, int base_log, int levels, const PbsArgs &a, cudaStream_t s) {
+    if (a.dbg && K == 4 && G == 3 && base_log == 8 && levels == 5) {   // per-phase cycle counts (TFA_PBS_TIMING=1)
+        const size_t smem = PbsSmemLayout<4, 3>::bytes;
+        cudaError_t e = set_smem(pbs_kernel<4, 3, 8, 5, true>, smem);
+        if (e != cudaSuccess) return e;
+        pbs_kernel<4, 3, 8, 5, true><<<(a.count + 2) / 3, CMUX_THREADS, smem, s>>>(a);
+        return cudaGetLastError();
+    }
     LAUNCH_PBS(4, 1, 8, 5) LAUNCH_PBS(4, 2, 8, 5) LAUNCH_PBS(4, 3, 8, 5)
     LAUNCH_PBS(1, 1, 8, 5) LAUNCH_PBS(1, 4, 8, 5) LAUNCH_PBS(1, 8, 8, 5)
     return cudaErrorInvalidValue;
@@ -325,7 +393,7 @@ cudaError_t launch_cmux_tree(int K, int G, int base_log, int levels, const TreeA
     return cudaErrorInvalidValue;
 }
 cudaError_t launch_fourier_convert(const ConvertArgs &a, cudaStream_t s) {
-    size_t smem = (size_t)(CMUX_GROUPS * XB_ELEMS + 512) * sizeof(cd);
+    size_t smem = (size_t)(CMUX_GROUPS * XB_ELEMS + 256) * sizeof(cd);
     cudaError_t e = set_smem(fourier_convert_kernel, smem);
     if (e != cudaSuccess) return e;
     long blocks = (a.npoly + CMUX_GROUPS - 1) / CMUX_GROUPS;

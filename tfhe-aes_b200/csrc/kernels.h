@@ -6,7 +6,7 @@
 struct PbsArgs {
     const uint64_t *lwe_in;   // [count][lwe_dim+1]
     const double2 *bsk;       // Fourier BSK [lwe_dim][level][row][col][p]
-    const double2 *tw;        // 512 twiddles (make_twiddle_tables)
+    const double2 *tw;        // 256 mid twiddles (make_twiddle_table)
     const uint64_t *lut;      // [N] body of the trivial accumulator
     uint64_t *out;            // [count][k*N+1]
     uint64_t in_scale;        // cleartext multiplier applied to the input before the modulus switch
@@ -14,6 +14,8 @@ struct PbsArgs {
     uint64_t post_add;        // added to the output body
     int lwe_dim;
     int count;
+    uint64_t *dbg;            // debug: per-phase cycle counters of block 0 (nullptr in production)
+    int stagger;              // cycles by which odd CTAs start late (spreads the L2 demand of the key rows)
 };
 struct VpArgs {
     const double2 *ggsw_f;    // [njobs][nbits][level][row][col][p], bit 0 = LSB

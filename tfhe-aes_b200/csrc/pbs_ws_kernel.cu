@@ -46,8 +46,7 @@ template <int K, int G>
 struct WsSmem {
     uint64_t acc[G][K + 1][POLY_N];
     cd xb[CMUX_GROUPS][XB_ELEMS];
-    cd twf[256];
-    cd twi[256];
+    cd tw[256];
     uint64_t full[K + 1];
     uint64_t empty[K + 1];
     uint64_t inv;
@@ -69,7 +68,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
     constexpr unsigned RING_BYTES = WS_RING * ROW_BYTES;
 
     // ---- prologue (all 512 threads) ---------------------------------------------------------------
-    for (int i = tid; i < 512; i += WS_THREADS) sm.twf[i] = a.tw[i];  // twf and twi are contiguous
+    for (int i = tid; i < 256; i += WS_THREADS) sm.tw[i] = a.tw[i];
     for (int idx = tid; idx < G * np; idx += WS_THREADS) {
         const int g = idx / np, i = idx % np;
         const int ct = min(ct0 + g, a.count - 1);
@@ -113,14 +112,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
                 load_decompose_rot<BASE_LOG, LEVELS>(sm.acc[ct][r], lane, ahat[ct * np + i], v, st_re, st_im);
 #pragma unroll 1
                 for (int lev = LEVELS; lev >= 1; lev--) {
-                    if (lev != LEVELS) next_digits<BASE_LOG>(v, st_re, st_im);
+                    if (lev != LEVELS) next_digits<BASE_LOG, LEVELS>(v, st_re, st_im, lev);
                     // the slots must have been consumed by the MAC warps (rows of the previous production)
                     if (produced > 0) {
                         mbar_wait(&sm.empty[r_a], (produced - 1) & 1);
                         if (r_b != r_a) mbar_wait(&sm.empty[r_b], (produced - 1) & 1);
                     }
                     __syncwarp();
-                    fft256_fwd_pass1(v, lane, sm.twf, sm.xb[gid]);
+                    fft256_fwd_pass1(v, lane, sm.tw, sm.xb[gid]);
                     __syncwarp();
                     fft256_fwd_pass2(v, lane, sm.xb[gid]);
                     __syncwarp();
@@ -136,7 +135,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
                 for (int k2 = 0; k2 < 16; k2++) v[k2] = sm.xb[gid][lane + 16 * k2];
                 fft256_inv_pass1_compute(v);
                 __syncwarp();
-                fft256_inv_pass1_store(v, lane, sm.twi, sm.xb[gid]);
+                fft256_inv_pass1_store(v, lane, sm.tw, sm.xb[gid]);
                 __syncwarp();
                 fft256_inv_pass2(v, lane, sm.xb[gid]);
                 if (active) {

@@ -1,10 +1,10 @@
-// twiddle_host.h — host-side construction of the 256-point mid-twiddle tables used by fft_core.cuh.
+// twiddle_host.h — host-side construction of the 256-point mid-twiddle table used by fft_core.cuh.
 #pragma once
 #include <cmath>
 #include "fft_core.cuh"
-// tw[0..255]   = twf[k1*16 + n2] = theta^(n2 (4 k1 + 1)),  theta = exp(2 pi i / 1024)
-// tw[256..511] = twi[n2*16 + k1] = conj(theta^(n2 (4 k1 + 1)))
-static inline void make_twiddle_tables(cd *tw) {
+// tw[xb_idx(k1, n2)] = theta^(n2 (4 k1 + 1)),  theta = exp(2 pi i / 1024)   (256 entries, swizzled like the
+// exchange buffers so that the forward and the inverse pass both read it without bank conflicts)
+static inline void make_twiddle_table(cd *tw) {
     const long double two_pi = 6.283185307179586476925286766559005768L;
     for (int k1 = 0; k1 < 16; k1++)
         for (int n2 = 0; n2 < 16; n2++) {
@@ -15,7 +15,6 @@ static inline void make_twiddle_tables(cd *tw) {
             if (e == 256) { c = 0.0; s = 1.0; }
             if (e == 512) { c = -1.0; s = 0.0; }
             if (e == 768) { c = 0.0; s = -1.0; }
-            tw[k1 * 16 + n2] = cmk(c, s);
-            tw[256 + n2 * 16 + k1] = cmk(c, -s);
+            tw[xb_idx(k1, n2)] = cmk(c, s);
         }
 }
