@@ -359,7 +359,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(B * state_words * 8), "steps": e2e_steps, "api": "tfa_aes_ctr (host buffers, pinned)"},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
-            "roofline": {"bound": "fp64", "kernel": "pbs_kernel<4,3,8,5>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
+            "roofline": {"bound": "fp64", "kernel": "pbs_ws_kernel<4,3,8,5>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
                          "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 figure)", "traffic": None,
                          "launch_ms": pbs_ms, "pbs_per_launch": count, "flop_per_pbs": PBS_FLOP,
                          "bsk_hbm_gbs": BSK_BYTES * -(-count // (3 * 148)) / (pbs_ms * 1e-3) * 1e-9, "hbm_peak_gbs": hbm,

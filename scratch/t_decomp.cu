@@ -7,8 +7,8 @@ __global__ void k(const uint64_t *x, double *d, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t st;
-    d[5 * i] = (double)decomp85_first(x[i], st) * 1.5;
-    for (int lev = 4; lev >= 1; lev--) d[5 * i + 5 - lev] = (double)decomp85_level(st, lev) * 1.5;
+    d[5 * i] = decomp85_first(x[i], st) * 1.5;
+    for (int lev = 4; lev >= 1; lev--) d[5 * i + 5 - lev] = decomp85_level(st, lev) * 1.5;
 }
 __global__ void kt(const double *v, uint64_t *o, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -45,10 +45,10 @@ int main() {
     cudaError_t e = cudaMemcpy(d.data(), dd, n * 40, cudaMemcpyDeviceToHost);
     int bad = 0;
     for (int i = 0; i < n; i++) {
-        uint32_t st; int h[5];
+        uint32_t st; double h[5];
         h[0] = decomp85_first(x[i], st);
         for (int lev = 4; lev >= 1; lev--) h[5 - lev] = decomp85_level(st, lev);
-        for (int j = 0; j < 5; j++) if (h[j] * 1.5 != d[5 * i + j]) { if (bad < 5) printf("x=%llx j=%d host %d dev %f\n", (unsigned long long)x[i], j, h[j], d[5 * i + j] / 1.5); bad++; }
+        for (int j = 0; j < 5; j++) if (h[j] * 1.5 != d[5 * i + j]) { if (bad < 5) printf("x=%llx j=%d host %f dev %f\n", (unsigned long long)x[i], j, h[j], d[5 * i + j] / 1.5); bad++; }
     }
     printf("decomp85 device vs host: %d mismatches (%s)\n", bad, cudaGetErrorString(e));
     return bad != 0;

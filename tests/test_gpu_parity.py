@@ -83,6 +83,23 @@ def test_bootstrap_matches_oracle(engine_test, oracle_test):
     assert np.array_equal(((ph + np.uint64(1 << 48)) >> np.uint64(49)) & np.uint64(1), msgs)
 
 
+@pytest.mark.parametrize("schedule", [1, 2])
+@pytest.mark.parametrize("count", [3, 9, 20])
+def test_bootstrap_both_kernel_schedules(engine_test, oracle_test, schedule, count):
+    """The phase-synchronous (1) and the warp-specialised (2) PBS kernels compute the same bootstrap; count 3 / 9 / 20
+    selects 1 / 4 / 8 ciphertexts per CTA at the test parameters."""
+    rng = np.random.default_rng(50 + count)
+    o = oracle_test
+    lut = rng.integers(0, 2 ** 64, 512, dtype=np.uint64)
+    lwe = o.encrypt_lwe_small(rng.integers(0, 2 ** 64, count, dtype=np.uint64))
+    engine_test.set_pbs_schedule(schedule)
+    try:
+        got = engine_test.bootstrap(lwe, lut)
+    finally:
+        engine_test.set_pbs_schedule(0)
+    assert torus_absdiff(o.phase_big(got), o.phase_big(o.bootstrap(lwe, lut))) < 2 ** 36
+
+
 def test_bootstrap_general_lut(engine_test, oracle_test):
     rng = np.random.default_rng(6)
     o = oracle_test
@@ -311,6 +328,31 @@ def test_opt_bootstrap_matches_oracle(engine_opt, oracle_opt):
     assert torus_absdiff(o.phase_big(got), o.phase_big(ref)) < 2 ** 36
     ph = o.phase_big(got) + np.uint64(1 << 48)
     assert np.array_equal(((ph + np.uint64(1 << 48)) >> np.uint64(49)) & np.uint64(1), msgs)
+
+
+@pytest.mark.parametrize("count", [150, 300])
+def test_opt_bootstrap_wave_both_schedules(engine_opt, oracle_opt, count):
+    """PARAM_OPT with 2 (count 150) and 3 (count 300) ciphertexts per CTA: both kernel schedules decrypt to the encrypted
+    bits, agree with each other on the phase, and a sample agrees with the oracle."""
+    o = oracle_opt
+    rng = np.random.default_rng(count)
+    msgs = rng.integers(0, 2, count).astype(np.uint64)
+    ks = o.keyswitch(o.encrypt_bits(msgs))
+    ks[:, -1] += np.uint64(1 << 62)
+    lut = np.full(512, (1 << 64) - (1 << 48), dtype=np.uint64)
+    res = {}
+    for schedule in (1, 2):
+        engine_opt.set_pbs_schedule(schedule)
+        try:
+            res[schedule] = engine_opt.bootstrap(ks, lut)
+        finally:
+            engine_opt.set_pbs_schedule(0)
+        ph = o.phase_big(res[schedule]) + np.uint64(1 << 48)
+        assert np.array_equal(((ph + np.uint64(1 << 48)) >> np.uint64(49)) & np.uint64(1), msgs)
+    assert torus_absdiff(o.phase_big(res[1]), o.phase_big(res[2])) < 2 ** 36
+    sample = [0, count // 2, count - 1]
+    ref = o.bootstrap(ks[sample], lut)
+    assert torus_absdiff(o.phase_big(res[2][sample]), o.phase_big(ref)) < 2 ** 36
 
 
 def test_opt_many_sbox_noise_within_tolerance(pkg, engine_opt, oracle_opt):

@@ -88,6 +88,7 @@ _SIGS = {
     "tfa_bootstrap_dev": [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p],
     "tfa_client_set_secret_keys": [C.c_void_p, C.c_void_p, C.c_void_p],
     "tfa_ctx_profile": [C.c_void_p, C.c_int],
+    "tfa_ctx_set_pbs_schedule": [C.c_void_p, C.c_int],
     "tfa_ctx_profile_report": [C.c_void_p, C.c_void_p, C.c_void_p],
     "tfa_measure_fp64_peak": [C.c_void_p, C.POINTER(C.c_double)],
     "tfa_lut_size": [C.c_void_p, C.c_int],
@@ -227,6 +228,10 @@ class Engine:
         self._ck(self.lib.tfa_ctx_synchronize(self.h))
 
     STAGES = ("ks_decompose", "ks_gemv", "pbs", "pfks_decompose", "pfks_gemv", "fourier", "vp", "cmux_tree", "linear", "misc")
+
+    def set_pbs_schedule(self, schedule):
+        """0 = automatic, 1 = phase-synchronous PBS kernel, 2 = warp-specialised PBS kernel."""
+        self._ck(self.lib.tfa_ctx_set_pbs_schedule(self.h, int(schedule)))
 
     def profile(self, enable=True):
         self._ck(self.lib.tfa_ctx_profile(self.h, int(enable)))

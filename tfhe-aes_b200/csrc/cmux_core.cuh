@@ -82,9 +82,11 @@ HD int decomp_next(uint32_t &state) {
 // All five digits at once: with r = 64 - 40 = 24, x' = x + 2^23 (closest representable) plus the
 // offset 128 * (1 + 2^8 + .. + 2^32) << 24 has, in bits 24..63, the bytes  d_j + 128  of a balanced digit set
 // d_j in [-128, 127] with  sum_j d_j 2^(8j) = closest(x) >> 24  (mod 2^40): adding 128 per byte lets the
-// carries of the signed recoding ripple in ONE 64-bit addition.  XOR with 0x80 per byte then turns
-// d_j + 128 into the two's-complement byte of d_j.  Digit of level 5 (least significant, consumed first) =
-// byte 3 of the low word; the high word holds levels 4, 3, 2, 1 in bytes 0..3.
+// carries of the signed recoding ripple in ONE 64-bit addition.  Digit of level 5 (least significant,
+// consumed first) = byte 3 of the low word; the high word holds levels 4, 3, 2, 1 in bytes 0..3.
+// Byte -> double without a conversion instruction (I2F.F64 issues at 1/4 of the FP64 rate on B200,
+// scratch/mb_xu.cu): the byte becomes the low mantissa bits of 2^52, and one exact subtraction of 2^52 + 128
+// leaves d_j.
 // Difference from tfhe-rs' iterator: an exact tie (digit = +-128) is always resolved to -128 (+1 carry)
 // where tfhe-rs picks by a state bit; both recodings represent the same value, so the external product is
 // the same up to the noise realisation.
@@ -92,25 +94,22 @@ HD int decomp_next(uint32_t &state) {
 #define USE_DECOMP85 1
 #endif
 #define DECOMP85_ADD 0x8080808080800000ull
-#define DECOMP85_XOR 0x8080808080000000ull
-HD int signed_byte(uint32_t w, int b) {
+HD double digit85(uint32_t w, int b) {
 #ifdef __CUDA_ARCH__
-    // prmt with sign replication (selector nibble 8|b); __byte_perm() masks that bit off, hence inline PTX
-    int r;
-    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(w), "r"(0x8880 + 0x1111 * b));
-    return r;
+    const uint32_t byte = __byte_perm(w, 0, 0x4440 + b);
+    return __hiloint2double(0x43300000, (int)byte) - 4503599627370624.0;   // (2^52 + byte) - (2^52 + 128)
 #else
-    return (int)(int8_t)(w >> (8 * b));
+    return (double)(int)((w >> (8 * b)) & 0xFF) - 128.0;
 #endif
 }
 // first digit (level 5) and the state word holding the other four
-HD int decomp85_first(uint64_t x, uint32_t &state) {
-    const uint64_t y = (x + DECOMP85_ADD) ^ DECOMP85_XOR;
+HD double decomp85_first(uint64_t x, uint32_t &state) {
+    const uint64_t y = x + DECOMP85_ADD;
     state = (uint32_t)(y >> 32);
-    return signed_byte((uint32_t)y, 3);
+    return digit85((uint32_t)y, 3);
 }
 // digit of level lev in 4..1
-HD int decomp85_level(uint32_t state, int lev) { return signed_byte(state, 4 - lev); }
+HD double decomp85_level(uint32_t state, int lev) { return digit85(state, 4 - lev); }
 
 // ---- phase A: build ct1 = (acc * X^rot - acc) [DIFF_ROTATE] or (ext - acc) [DIFF_EXTERNAL] for the
 // 32 coefficients this lane owns, start the decomposition, emit the digits of the first level into v.
@@ -144,15 +143,15 @@ HD void phase_load_decompose(int tid, CmuxSmem<K, G> &sm, CmuxRegs<K, G> &rg, co
             a0 = e[j] - poly[j];
             a1 = e[j + POLY_M] - poly[j + POLY_M];
         }
-        int d0, d1;
+        double d0, d1;
         if (USE_DECOMP85 && BASE_LOG == 8 && LEVELS == 5) {
             d0 = decomp85_first(a0, rg.st_re[n1]);
             d1 = decomp85_first(a1, rg.st_im[n1]);
         } else {
-            d0 = decomp_first<BASE_LOG, LEVELS>(a0, rg.st_re[n1]);
-            d1 = decomp_first<BASE_LOG, LEVELS>(a1, rg.st_im[n1]);
+            d0 = (double)decomp_first<BASE_LOG, LEVELS>(a0, rg.st_re[n1]);
+            d1 = (double)decomp_first<BASE_LOG, LEVELS>(a1, rg.st_im[n1]);
         }
-        rg.v[n1] = cmk((double)d0, (double)d1);
+        rg.v[n1] = cmk(d0, d1);
     }
 }
 // register-only forms used by the warp-specialised PBS kernel (no Fourier accumulators in the FFT warps)
@@ -169,15 +168,15 @@ HD void load_decompose_rot(const uint64_t *poly, int lane, int rot, cd (&v)[16],
         const uint64_t m1 = (uint64_t)0 - (uint64_t)(((s >> 9) ^ (s >> 8)) & 1);
         const uint64_t a0 = ((x0 ^ m0) - m0) - poly[j];
         const uint64_t a1 = ((x1 ^ m1) - m1) - poly[j + POLY_M];
-        int d0, d1;
+        double d0, d1;
         if (USE_DECOMP85 && BASE_LOG == 8 && LEVELS == 5) {
             d0 = decomp85_first(a0, st_re[n1]);
             d1 = decomp85_first(a1, st_im[n1]);
         } else {
-            d0 = decomp_first<BASE_LOG, LEVELS>(a0, st_re[n1]);
-            d1 = decomp_first<BASE_LOG, LEVELS>(a1, st_im[n1]);
+            d0 = (double)decomp_first<BASE_LOG, LEVELS>(a0, st_re[n1]);
+            d1 = (double)decomp_first<BASE_LOG, LEVELS>(a1, st_im[n1]);
         }
-        v[n1] = cmk((double)d0, (double)d1);
+        v[n1] = cmk(d0, d1);
     }
 }
 // digits of level lev (LEVELS-1 .. 1; levels are consumed in decreasing order)
@@ -185,15 +184,15 @@ template <int BASE_LOG, int LEVELS>
 HD void next_digits(cd (&v)[16], uint32_t (&st_re)[16], uint32_t (&st_im)[16], int lev) {
 #pragma unroll
     for (int n1 = 0; n1 < 16; n1++) {
-        int d0, d1;
+        double d0, d1;
         if (USE_DECOMP85 && BASE_LOG == 8 && LEVELS == 5) {
             d0 = decomp85_level(st_re[n1], lev);
             d1 = decomp85_level(st_im[n1], lev);
         } else {
-            d0 = decomp_next<BASE_LOG>(st_re[n1]);
-            d1 = decomp_next<BASE_LOG>(st_im[n1]);
+            d0 = (double)decomp_next<BASE_LOG>(st_re[n1]);
+            d1 = (double)decomp_next<BASE_LOG>(st_im[n1]);
         }
-        v[n1] = cmk((double)d0, (double)d1);
+        v[n1] = cmk(d0, d1);
     }
 }
 template <int K, int G, int BASE_LOG, int LEVELS>

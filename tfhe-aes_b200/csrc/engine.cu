@@ -79,6 +79,7 @@ extern "C" int tfa_ctx_create(const tfa_params *p, int device, void *stream, tfa
     ctx->device = device;
     ctx->launches = 0;
     ctx->profiling = false;
+    ctx->pbs_schedule = 0;
     ctx->own_stream = (stream == nullptr);
     ctx->stream = (cudaStream_t)stream;
     ctx->bsk_f = nullptr; ctx->ksk = nullptr; ctx->pfpksk = nullptr; ctx->kp_ksk = nullptr; ctx->kp_pfpksk = nullptr;
@@ -112,6 +113,12 @@ extern "C" void tfa_ctx_destroy(tfa_ctx *ctx) {
 }
 extern "C" const char *tfa_last_error(const tfa_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 extern "C" int tfa_ctx_synchronize(tfa_ctx *ctx) { CU(cudaStreamSynchronize(ctx->stream)); return TFA_OK; }
+extern "C" int tfa_ctx_set_pbs_schedule(tfa_ctx *ctx, int schedule) {
+    if (schedule < 0 || schedule > 2) return ctx->fail(TFA_ERR_PARAM, "pbs schedule must be 0 (auto), 1 (phase-synchronous) or 2 (warp-specialised)");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->pbs_schedule = schedule;
+    return TFA_OK;
+}
 extern "C" uint64_t tfa_ctx_launch_count(const tfa_ctx *ctx) { return ctx->launches; }
 
 // ------------------------------------------------------------------------------------------------
@@ -254,33 +261,38 @@ int dev_pbs(tfa_ctx *ctx, const u64 *in, int count, const u64 *lut, u64 in_scale
     PbsArgs a{};
     a.lwe_in = in; a.bsk = ctx->bsk_f; a.tw = ctx->tw; a.lut = lut; a.out = out;
     a.in_scale = in_scale; a.pre_add_body = pre_add; a.post_add = post_add; a.lwe_dim = ctx->n; a.count = count;
-    // Two schedules of the same arithmetic (measured on B200, 669 steps): with one ciphertext per CTA the
-    // warp-specialised kernel wins (9.7 vs 11.0 ms per wave: FFT and multiply-accumulate overlap); with 2-3
-    // ciphertexts per CTA the phase-synchronous kernel wins (13.9 vs 15.8 ms at G = 3: its single hand-over
-    // buffer makes the two roles wait for each other, and a second buffer does not fit in shared memory).
+    // Two schedules of the same arithmetic (measured on B200, PARAM_OPT, 669 steps, one wave of 148 CTAs):
+    //   warp-specialised (pbs_ws_kernel.cu): 10.85 ms at G = 3, 9.9 ms at G = 2, 7.7 ms at G = 1
+    //   phase-synchronous (fp_kernels.cu):   13.1 ms at G = 3
+    // The warp-specialised kernel is the default wherever it is instantiated; the phase-synchronous one serves the
+    // remaining shapes (K = 1 test parameter sets with G > 1) and stays selectable for comparison.
     const int G = pick_G(ctx->k, count);
     static const int stagger = getenv("TFA_PBS_STAGGER") ? atoi(getenv("TFA_PBS_STAGGER")) : 0;
     a.stagger = stagger;
     static const bool timing = getenv("TFA_PBS_TIMING") != nullptr;
+    const bool ws_available = true;   // every (K, G) pick_G returns is instantiated in both kernels
+    const bool use_ws = ws_available && ctx->pbs_schedule != 1;
     if (timing && G == 3 && ctx->k == 4) {
-        // debug aid: per-phase clock64() totals of thread 0 of block 0, printed to stderr
+        // debug aid: per-phase clock64() totals of block 0 (one thread per role)
         uint64_t *d = nullptr, h[16] = {0};
         CU(cudaMalloc(&d, sizeof(h)));
+        CU(cudaMemsetAsync(d, 0, sizeof(h), ctx->stream));
         a.dbg = d;
-        CU(launch_pbs(ctx->k, G, ctx->p.pbs_base_log, ctx->p.pbs_level, a, ctx->stream));
+        if (use_ws) CU(launch_pbs_ws(ctx->k, G, ctx->p.pbs_base_log, ctx->p.pbs_level, a, ctx->stream));
+        else CU(launch_pbs(ctx->k, G, ctx->p.pbs_base_log, ctx->p.pbs_level, a, ctx->stream));
         CU(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         cudaFree(d);
         static const char *nm[9] = {"decompose", "fwd_fft", "bar_after_fwd", "wait_full", "mac", "bar_after_mac", "inv0+bar", "inv_fft", "bar_end"};
-        uint64_t tot = 0;
-        for (int k = 0; k < 9; k++) tot += h[k];
-        fprintf(stderr, "[pbs timing] cycles per CMux step (thread 0, block 0), total %.0f:", (double)tot / ctx->n);
-        for (int k = 0; k < 9; k++) fprintf(stderr, " %s=%.0f", nm[k], (double)h[k] / ctx->n);
+        static const char *nw[9] = {"F:decompose", "F:digits+pass1", "F:wait_empty", "F:store+pass2+store", "F:wait_inv", "F:inverse",
+                                    "M:wait", "M:mac", "M:handover"};
+        fprintf(stderr, "[pbs timing] cycles per CMux step (block 0):");
+        for (int k = 0; k < 9; k++) fprintf(stderr, " %s=%.0f", use_ws ? nw[k] : nm[k], (double)h[k] / ctx->n);
         fprintf(stderr, "\n");
         ctx->launches++;
         return TFA_OK;
     }
-    if (G == 1) CU(launch_pbs_ws(ctx->k, G, ctx->p.pbs_base_log, ctx->p.pbs_level, a, ctx->stream));
+    if (use_ws) CU(launch_pbs_ws(ctx->k, G, ctx->p.pbs_base_log, ctx->p.pbs_level, a, ctx->stream));
     else CU(launch_pbs(ctx->k, G, ctx->p.pbs_base_log, ctx->p.pbs_level, a, ctx->stream));
     ctx->launches++;
     return TFA_OK;

@@ -97,6 +97,18 @@ HD void fft256_fwd_pass1(cd (&v)[16], int lane, const cd *tw, cd *xb) {
 #pragma unroll
     for (int k1 = 0; k1 < 16; k1++) xb[xb_idx(k1, lane)] = cmul(v[rev4(k1)], tw[xb_idx(k1, lane)]);
 }
+// the same in two halves, so that the arithmetic can run before the exchange buffer is free
+HD void fft256_fwd_pass1_compute(cd (&v)[16], int lane, const cd *tw) {
+#pragma unroll
+    for (int n1 = 1; n1 < 16; n1++) v[n1] = mul_w64<1>(v[n1], n1);
+    fft16<1>(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) v[rev4(k1)] = cmul(v[rev4(k1)], tw[xb_idx(k1, lane)]);
+}
+HD void fft256_fwd_pass1_store(const cd (&v)[16], int lane, cd *xb) {
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) xb[xb_idx(k1, lane)] = v[rev4(k1)];
+}
 // lane = k1.  Out: X[lane + 16 k2] at v[rev4(k2)]
 HD void fft256_fwd_pass2(cd (&v)[16], int lane, const cd *xb) {
 #pragma unroll

@@ -2,88 +2,128 @@
 //
 // Same arithmetic as pbs_kernel (fp_kernels.cu / cmux_core.cuh), different schedule.  One CTA of 512
 // threads holds G ciphertexts for all n CMux steps:
-//   warps 0-7  "FFT warps" : per step: rotate-subtract + signed decomposition, per level a forward FFT of
+//   warps 8-15 "FFT warps" : per step: rotate-subtract + signed decomposition, per level a forward FFT of
 //                            every digit polynomial into its hand-over slot, then the K+1 inverse FFTs and the
 //                            accumulator update.  Each 16-lane group owns polynomial (ct, r) and only ever
 //                            touches its own accumulator polynomial and its own slot, so FFT groups never wait
 //                            for each other (warp-level syncs only).
-//   warps 8-15 "MAC warps" : thread p owns Fourier point p of all G ciphertexts and multiplies row r of the
+//   warps 0-7  "MAC warps" : thread p owns Fourier point p of all G ciphertexts and multiplies row r of the
 //                            current level as soon as the G slots (*, r) are full, while the FFT warps already
-//                            work on the next level.  The Fourier bootstrap key is streamed L2 -> shared memory
-//                            by a thread-private cp.async ring (BSK_RING rows ahead, all CTAs in step).
-// The two roles have different register needs (FFT: 16 complex + 32 decomposition states; MAC: G*(K+1)
-// complex accumulators), so the register file is re-balanced with setmaxnreg (152 / 104 per thread):
-// four warps per scheduler instead of two, and FP64 (FFT, MAC), ALU (decomposition) and LSU phases of the
-// two roles overlap instead of alternating.
-// Hand-shake per row r (mbarriers in shared memory): FULL[r] (G*16 FFT lanes arrive, MAC threads wait),
-// EMPTY[r] (256 MAC threads arrive, the FFT lanes of row r wait), INV (MAC threads arrive after leaving the
-// Fourier accumulators in the slots, FFT lanes wait).
+//                            work on the next level (the first pass of the next FFT runs in registers before
+//                            the slot is free).
+// The FFT phases are FP64-pipe bound and the multiply-accumulate is shared-memory bound (it reads 52 KB per row
+// for 60 FMAs per thread), so the two roles use complementary resources; run in separate warps they overlap
+// instead of alternating, with four warps per scheduler instead of two.  The roles have different register
+// needs (FFT: 16 complex + 32 decomposition states; MAC: G*(K+1) complex accumulators), so the register file
+// is re-balanced with setmaxnreg (144 / 112 per thread at G = 3).
+//
+// Bootstrap key: rows [col][p] of (K+1) x 4 KB, stored in consumption order, streamed L2 -> shared memory by
+// the TMA engine (cp.async.bulk, one lane per row) into a ring of K+1 slots (one level); BFULL[r] counts the
+// bytes of a row, BEMPTY[r] one arrival per MAC warp; the producer role rotates over the MAC warps and refills
+// the slot released one row earlier.
+// Hand-shake per row r (mbarriers in shared memory): RFULL[r] (one arrival per FFT group (ct, r), MAC threads
+// wait), REMPTY[r] (one arrival per MAC warp, the FFT lanes of row r wait before they overwrite their slot),
+// INV (MAC warps arrive after leaving the Fourier accumulators in the slots, FFT lanes wait).
 #include "cmux_core.cuh"
 #include "kernels.h"
 
 #define WS_THREADS 512
 #define WS_FFT_THREADS 256
-#define WS_RING 4
+#define WS_MAC_WARPS ((WS_THREADS - WS_FFT_THREADS) / 32)
 
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+__device__ __forceinline__ unsigned ws_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ws_mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ws_smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+__device__ __forceinline__ void ws_mbar_arrive(uint64_t *bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(ws_smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
-    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+__device__ __forceinline__ void ws_mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(ws_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_wait(uint64_t *bar, unsigned parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra.uni WAIT_DONE;\n\t"
         "bra.uni WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(addr), "r"(parity) : "memory");
+        "WAIT_DONE:\n\t}" ::"r"(ws_smem_u32(bar)), "r"(parity) : "memory");
+}
+// wait for two barriers with one polling loop (the two try_wait latencies overlap)
+__device__ __forceinline__ void ws_mbar_wait2(uint64_t *bar_a, unsigned parity_a, uint64_t *bar_b, unsigned parity_b) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "WAIT2_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%2], %3;\n\t"
+        "and.pred p, p, q;\n\t"
+        "@p bra.uni WAIT2_DONE;\n\t"
+        "bra.uni WAIT2_LOOP;\n\t"
+        "WAIT2_DONE:\n\t}" ::"r"(ws_smem_u32(bar_a)), "r"(parity_a), "r"(ws_smem_u32(bar_b)), "r"(parity_b) : "memory");
+}
+__device__ __forceinline__ void ws_bulk_copy_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ws_smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(ws_smem_u32(bar))
+                 : "memory");
 }
 
 template <int K, int G>
 struct WsSmem {
-    uint64_t acc[G][K + 1][POLY_N];
-    cd xb[CMUX_GROUPS][XB_ELEMS];
-    cd tw[256];
-    uint64_t full[K + 1];
-    uint64_t empty[K + 1];
+    uint64_t acc[G][K + 1][POLY_N];      // the G accumulators (GLWE, standard domain)
+    cd hs[(K + 1) * G][XB_ELEMS];        // hand-over slots: spectrum / Fourier accumulator of (ct, r) at [r * G + ct]
+    cd tw[256];                          // mid twiddles, swizzled (fft_core.cuh)
+    cd ring[K + 1][K + 1][POLY_M];       // one level of the Fourier bootstrap key: [row][col][p]
+    uint64_t rfull[K + 1];
+    uint64_t rempty[K + 1];
+    uint64_t bfull[K + 1];
+    uint64_t bempty[K + 1];
     uint64_t inv;
     uint64_t pad_;
 };
 
-template <int K, int G, int BASE_LOG, int LEVELS>
+// modulus switch to 2N: a~ = (a * in_scale [+ pre_add on the body] + 2^53) >> 54
+__device__ __forceinline__ int ws_mod_switch_2n(const PbsArgs &a, int ct, int i) {
+    uint64_t x = a.lwe_in[(size_t)ct * (a.lwe_dim + 1) + i] * a.in_scale;
+    if (i == a.lwe_dim) x += a.pre_add_body;
+    return (int)((x + (1ull << 53)) >> 54) & (2 * POLY_N - 1);
+}
+
+// TIMING (debug launches, PbsArgs::dbg != nullptr): thread 0 (FFT role) and thread 256 (MAC role) of block 0 accumulate
+// clock64() deltas per activity and write them to dbg[0..WT_COUNT).
+enum { WT_F_DECOMP, WT_F_PASS1, WT_F_WAIT_EMPTY, WT_F_POST, WT_F_WAIT_INV, WT_F_INV, WT_M_WAIT, WT_M_MAC, WT_M_HANDOVER, WT_COUNT };
+template <int K, int G, int BASE_LOG, int LEVELS, bool TIMING = false>
 __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    long long tacc[6] = {0, 0, 0, 0, 0, 0};
+    long long tlast = TIMING ? clock64() : 0;
+#define WT(k) do { if (TIMING) { const long long t_ = clock64(); tacc[(k) % 6] += t_ - tlast; tlast = t_; } } while (0)
     WsSmem<K, G> &sm = *reinterpret_cast<WsSmem<K, G> *>(smem_raw);
-    cd *ring = reinterpret_cast<cd *>(smem_raw + sizeof(WsSmem<K, G>));              // [WS_RING][K+1][256]
-    uint16_t *ahat = reinterpret_cast<uint16_t *>(ring + WS_RING * POLY_M * (K + 1));
     const int tid = threadIdx.x;
-    const int n = a.lwe_dim, np = a.lwe_dim + 1;
+    const int n = a.lwe_dim;
     const int ct0 = blockIdx.x * G;
+    constexpr int RING = K + 1;
     constexpr int ROWS = LEVELS * (K + 1);
-    constexpr size_t ROW_ELEMS = (size_t)POLY_M * (K + 1);
+    constexpr int ROW_ELEMS = POLY_M * (K + 1);
     constexpr unsigned ROW_BYTES = (unsigned)(ROW_ELEMS * sizeof(cd));
-    constexpr unsigned RING_BYTES = WS_RING * ROW_BYTES;
+    const int nrows = n * ROWS;
+    // register split (per thread, 8 + 8 warps, 128 on average): the MAC role holds G*(K+1) complex accumulators
+    constexpr int MAC_REGS = G >= 3 ? 112 : (G == 2 ? 96 : 72);
 
     // ---- prologue (all 512 threads) ---------------------------------------------------------------
     for (int i = tid; i < 256; i += WS_THREADS) sm.tw[i] = a.tw[i];
-    for (int idx = tid; idx < G * np; idx += WS_THREADS) {
-        const int g = idx / np, i = idx % np;
-        const int ct = min(ct0 + g, a.count - 1);
-        uint64_t x = a.lwe_in[(size_t)ct * np + i] * a.in_scale;
-        if (i == n) x += a.pre_add_body;
-        ahat[g * np + i] = (uint16_t)((x + (1ull << 53)) >> 54);  // modulus switch to 2N
-    }
     if (tid == 0) {
-        for (int r = 0; r <= K; r++) { mbar_init(&sm.full[r], G * 16); mbar_init(&sm.empty[r], WS_THREADS - WS_FFT_THREADS); }
-        mbar_init(&sm.inv, WS_THREADS - WS_FFT_THREADS);
+        for (int r = 0; r <= K; r++) {
+            ws_mbar_init(&sm.rfull[r], G);
+            ws_mbar_init(&sm.rempty[r], WS_MAC_WARPS);
+            ws_mbar_init(&sm.bfull[r], 1);
+            ws_mbar_init(&sm.bempty[r], WS_MAC_WARPS);
+        }
+        ws_mbar_init(&sm.inv, WS_MAC_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
     for (int g = 0; g < G; g++) {
-        const int rot = (2 * POLY_N - ahat[g * np + n]) & (2 * POLY_N - 1);
+        const int rot = (2 * POLY_N - ws_mod_switch_2n(a, min(ct0 + g, a.count - 1), n)) & (2 * POLY_N - 1);
         for (int idx = tid; idx < (K + 1) * POLY_N; idx += WS_THREADS) {
             const int r = idx / POLY_N, j = idx % POLY_N;
             sm.acc[g][r][j] = (r == K) ? rotated_coef(a.lut, j, rot) : 0;
@@ -91,53 +131,70 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
     }
     __syncthreads();
 
-    if (tid < WS_FFT_THREADS) {
+    // Role by warp index: the MAC role takes warps 0-7 and the FFT role warps 8-15.  The FFT warps are the critical
+    // path (they carry 64 % of the FP64 work plus all integer work), and the issue arbiter favours the higher
+    // warp ids when several warps of a scheduler are eligible.
+    if (tid >= WS_THREADS - WS_FFT_THREADS) {
         // ================================ FFT warps ================================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
-        const int gid = tid >> 4, lane = tid & 15;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(256 - MAC_REGS));
+        const int ftid = tid - (WS_THREADS - WS_FFT_THREADS);
+        const int gid = ftid >> 4, lane = ftid & 15;
         const bool active = gid < G * (K + 1);
-        const int ct = active ? gid / (K + 1) : 0, r = active ? gid % (K + 1) : 0;
+        // group -> polynomial: row-major (r = gid / G, ct = gid % G), so that the two groups of a warp own the same
+        // or adjacent rows and the warp-uniform wait below never holds a row-r group back until row r+2 is consumed
+        const int ct = active ? gid % G : 0, r = active ? gid / G : 0;
         // Both 16-lane groups of a warp execute ONE instruction stream (a diverged half-warp would pay a full
         // issue slot and a full FP64 pipe pass for 16 lanes): waits are made warp-uniform by waiting for the
-        // rows of both groups; an idle group (gid >= G*(K+1)) runs along on its own scratch slot.
-        const int gid_a = (tid >> 5) * 2, gid_b = gid_a + 1;
-        const int r_a = gid_a % (K + 1);
-        const int r_b = (gid_b < G * (K + 1)) ? gid_b % (K + 1) : r_a;
+        // rows of both groups; an idle group (gid >= G*(K+1)) runs along with its stores predicated off.
+        const int gid_a = (ftid >> 5) * 2, gid_b = gid_a + 1;
+        const int r_a = gid_a / G;
+        const int r_b = (gid_b < G * (K + 1)) ? gid_b / G : r_a;
+        cd *slot = sm.hs[active ? gid : 0];
+        const int my_ct = min(ct0 + ct, a.count - 1);
         cd v[16];
         uint32_t st_re[16], st_im[16];
-        unsigned produced = 0;                    // productions into this group's slot so far
+        unsigned produced = 0;                    // levels this group has produced so far
         if (gid_a < G * (K + 1)) {
+            int rot = ws_mod_switch_2n(a, my_ct, 0);
 #pragma unroll 1
             for (int i = 0; i < n; i++) {
-                load_decompose_rot<BASE_LOG, LEVELS>(sm.acc[ct][r], lane, ahat[ct * np + i], v, st_re, st_im);
+                // the mask element of the next step is fetched one step ahead (its latency hides behind a CMux)
+                const int rot_next = (i + 1 < n) ? ws_mod_switch_2n(a, my_ct, i + 1) : 0;
+                load_decompose_rot<BASE_LOG, LEVELS>(sm.acc[ct][r], lane, rot, v, st_re, st_im);
+                rot = rot_next;
+                WT(WT_F_DECOMP);
 #pragma unroll 1
                 for (int lev = LEVELS; lev >= 1; lev--) {
                     if (lev != LEVELS) next_digits<BASE_LOG, LEVELS>(v, st_re, st_im, lev);
-                    // the slots must have been consumed by the MAC warps (rows of the previous production)
-                    if (produced > 0) {
-                        mbar_wait(&sm.empty[r_a], (produced - 1) & 1);
-                        if (r_b != r_a) mbar_wait(&sm.empty[r_b], (produced - 1) & 1);
+                    // first pass in registers; only then wait until the MAC warps have consumed the previous
+                    // occupant of the slot (rows of the previous production)
+                    fft256_fwd_pass1_compute(v, lane, sm.tw);
+                    WT(WT_F_PASS1);
+                    if (produced > 0) ws_mbar_wait2(&sm.rempty[r_a], (produced - 1) & 1, &sm.rempty[r_b], (produced - 1) & 1);
+                    WT(WT_F_WAIT_EMPTY);
+                    if (active) fft256_fwd_pass1_store(v, lane, slot);
+                    __syncwarp();
+                    fft256_fwd_pass2(v, lane, slot);
+                    __syncwarp();
+                    if (active) {
+#pragma unroll
+                        for (int k2 = 0; k2 < 16; k2++) slot[lane + 16 * k2] = v[rev4(k2)];
                     }
                     __syncwarp();
-                    fft256_fwd_pass1(v, lane, sm.tw, sm.xb[gid]);
-                    __syncwarp();
-                    fft256_fwd_pass2(v, lane, sm.xb[gid]);
-                    __syncwarp();
-#pragma unroll
-                    for (int k2 = 0; k2 < 16; k2++) sm.xb[gid][lane + 16 * k2] = v[rev4(k2)];
-                    if (active) mbar_arrive(&sm.full[r]);
+                    if (active && lane == 0) ws_mbar_arrive(&sm.rfull[r]);
                     produced++;
+                    WT(WT_F_POST);
                 }
                 // inverse transform of the Fourier accumulator the MAC warps left in this group's slot
-                mbar_wait(&sm.inv, i & 1);
-                __syncwarp();
+                ws_mbar_wait(&sm.inv, i & 1);
+                WT(WT_F_WAIT_INV);
 #pragma unroll
-                for (int k2 = 0; k2 < 16; k2++) v[k2] = sm.xb[gid][lane + 16 * k2];
+                for (int k2 = 0; k2 < 16; k2++) v[k2] = slot[lane + 16 * k2];
                 fft256_inv_pass1_compute(v);
                 __syncwarp();
-                fft256_inv_pass1_store(v, lane, sm.tw, sm.xb[gid]);
+                if (active) fft256_inv_pass1_store(v, lane, sm.tw, slot);
                 __syncwarp();
-                fft256_inv_pass2(v, lane, sm.xb[gid]);
+                fft256_inv_pass2(v, lane, slot);
                 if (active) {
                     uint64_t *poly = sm.acc[ct][r];
 #pragma unroll
@@ -148,34 +205,26 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
                     }
                 }
                 __syncwarp();
+                WT(WT_F_INV);
             }
+            if (TIMING && blockIdx.x == 0 && ftid == 0)
+                for (int k = 0; k < 6; k++) a.dbg[k] = (uint64_t)tacc[k];
         }
     } else {
         // ================================ MAC warps ================================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-        const int p = tid - WS_FFT_THREADS;
-        // bootstrap-key ring: thread-private slots, filled WS_RING rows ahead (key stored in consumption order)
-        const cd *pf_src = a.bsk + p;
-        long pf_left = (long)n * ROWS;
-        const unsigned ring_u32 = (unsigned)__cvta_generic_to_shared(ring) + p * (unsigned)sizeof(cd);
-        unsigned pf_off = 0, rd_off = 0;
-        auto issue = [&]() {
-            if (pf_left > 0) {
-#pragma unroll
-                for (int c = 0; c <= K; c++)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(ring_u32 + pf_off + c * (POLY_M * (unsigned)sizeof(cd))),
-                                 "l"(pf_src + c * POLY_M));
-                pf_src += ROW_ELEMS;
-                pf_left--;
-                pf_off += ROW_BYTES;
-                if (pf_off == RING_BYTES) pf_off = 0;
-            }
-            asm volatile("cp.async.commit_group;\n" ::);
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MAC_REGS));
+        const int p = tid;
+        const int mwarp = p >> 5, mlane = p & 31;
+        auto produce = [&](int q) {               // fetch key row q into slot q % RING (the caller knows it is free)
+            const int s = q % RING;
+            ws_mbar_arrive_expect_tx(&sm.bfull[s], ROW_BYTES);
+            ws_bulk_copy_g2s(&sm.ring[s][0][0], a.bsk + (size_t)q * ROW_ELEMS, ROW_BYTES, &sm.bfull[s]);
         };
-#pragma unroll
-        for (int s = 0; s < WS_RING; s++) issue();
+        if (p == 0)
+            for (int q = 0; q < RING; q++) produce(q);   // nrows >= RING always
         cd facc[G][K + 1];
         unsigned level_count = 0;
+        int q = 0;                                // next key row to consume
 #pragma unroll 1
         for (int i = 0; i < n; i++) {
 #pragma unroll
@@ -186,23 +235,32 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
             for (int lev = LEVELS; lev >= 1; lev--) {
                 const unsigned parity = level_count & 1;
 #pragma unroll
-                for (int r = 0; r <= K; r++) {
-                    asm volatile("cp.async.wait_group %0;\n" ::"n"(WS_RING - 1) : "memory");
-                    const cd *w_ptr = reinterpret_cast<const cd *>(reinterpret_cast<const unsigned char *>(ring) + rd_off) + p;
-                    mbar_wait(&sm.full[r], parity);
+                for (int r = 0; r <= K; r++, q++) {
+                    ws_mbar_wait2(&sm.bfull[r], parity, &sm.rfull[r], parity);
+                    WT(WT_M_WAIT);
                     cd x[G];
 #pragma unroll
-                    for (int g = 0; g < G; g++) x[g] = sm.xb[g * (K + 1) + r][p];
+                    for (int g = 0; g < G; g++) x[g] = sm.hs[r * G + g][p];
 #pragma unroll
                     for (int c = 0; c <= K; c++) {   // key values are streamed one at a time (register budget)
-                        const cd w = w_ptr[c * POLY_M];
+                        const cd w = sm.ring[r][c][p];
 #pragma unroll
                         for (int g = 0; g < G; g++) cmac(facc[g][c], x[g], w);
                     }
-                    if (lev > 1) mbar_arrive(&sm.empty[r]);   // after the last level the slot is released below
-                    rd_off += ROW_BYTES;
-                    if (rd_off == RING_BYTES) rd_off = 0;
-                    issue();
+                    __syncwarp();
+                    if (mlane == 0) {
+                        // this warp's reads of the row are complete (their values fed the FMAs above)
+                        ws_mbar_arrive(&sm.bempty[r]);
+                        if (lev > 1) ws_mbar_arrive(&sm.rempty[r]);   // after the last level the slot is released below
+                        // refill the key slot released one row earlier, once every MAC warp is done with it
+                        if (mwarp == (q & (WS_MAC_WARPS - 1)) && q >= 1 && q - 1 + RING < nrows) {
+                            const int ps = (r + K) % RING;                              // slot of row q - 1
+                            const unsigned pp = (r == 0) ? (parity ^ 1) : parity;       // its level
+                            ws_mbar_wait(&sm.bempty[ps], pp);
+                            produce(q - 1 + RING);
+                        }
+                    }
+                    WT(WT_M_MAC);
                 }
                 level_count++;
             }
@@ -211,13 +269,21 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
 #pragma unroll
             for (int g = 0; g < G; g++)
 #pragma unroll
-                for (int c = 0; c <= K; c++) sm.xb[g * (K + 1) + c][p] = facc[g][c];
-            mbar_arrive(&sm.inv);
+                for (int c = 0; c <= K; c++) sm.hs[c * G + g][p] = facc[g][c];
+            __syncwarp();
+            if (mlane == 0) {
+                ws_mbar_arrive(&sm.inv);
+                // the slots are free again once the FFT lanes have read them (they wait on INV first, and only
+                // the owner group of a slot ever writes it)
 #pragma unroll
-            for (int r = 0; r <= K; r++) mbar_arrive(&sm.empty[r]);  // the slots are free again once the FFT lanes have read them (they wait on INV first)
+                for (int r = 0; r <= K; r++) ws_mbar_arrive(&sm.rempty[r]);
+            }
+            WT(WT_M_HANDOVER);
         }
-        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        if (TIMING && blockIdx.x == 0 && p == 0)
+            for (int k = 6; k < WT_COUNT; k++) a.dbg[k] = (uint64_t)tacc[k % 6];
     }
+#undef WT
     __syncthreads();
     // sample extract of coefficient 0
     for (int g = 0; g < G; g++) {
@@ -233,14 +299,21 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
 
 #define LAUNCH_WS(k, g, bl, lv)                                                                         \
     if (K == k && G == g && base_log == bl && levels == lv) {                                           \
-        size_t smem = sizeof(WsSmem<k, g>) + (size_t)WS_RING * POLY_M * (k + 1) * sizeof(cd) +              \
-                      (size_t)g * (a.lwe_dim + 1) * sizeof(uint16_t);                                  \
+        const size_t smem = sizeof(WsSmem<k, g>);                                                       \
         cudaError_t e = cudaFuncSetAttribute(pbs_ws_kernel<k, g, bl, lv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e;                                                                 \
         pbs_ws_kernel<k, g, bl, lv><<<(a.count + g - 1) / g, WS_THREADS, smem, s>>>(a);                 \
         return cudaGetLastError();                                                                      \
     }
 cudaError_t launch_pbs_ws(int K, int G, int base_log, int levels, const PbsArgs &a, cudaStream_t s) {
-    LAUNCH_WS(4, 1, 8, 5) LAUNCH_WS(1, 1, 8, 5)
+    if (a.dbg && K == 4 && G == 3 && base_log == 8 && levels == 5) {   // per-activity cycle counts (TFA_PBS_TIMING=1)
+        const size_t smem = sizeof(WsSmem<4, 3>);
+        cudaError_t e = cudaFuncSetAttribute(pbs_ws_kernel<4, 3, 8, 5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        pbs_ws_kernel<4, 3, 8, 5, true><<<(a.count + 2) / 3, WS_THREADS, smem, s>>>(a);
+        return cudaGetLastError();
+    }
+    LAUNCH_WS(4, 1, 8, 5) LAUNCH_WS(4, 2, 8, 5) LAUNCH_WS(4, 3, 8, 5)
+    LAUNCH_WS(1, 1, 8, 5) LAUNCH_WS(1, 4, 8, 5) LAUNCH_WS(1, 8, 8, 5)
     return cudaErrorInvalidValue;
 }
