@@ -131,6 +131,7 @@ extern "C" int tfa_ctx_alloc_keys(tfa_ctx *ctx) {
     CU(cudaMalloc(&ctx->bsk_f, ctx->bsk_f_bytes()));
     CU(cudaMalloc(&ctx->kp_ksk, ctx->kp_ksk_bytes()));
     CU(cudaMalloc(&ctx->kp_pfpksk, ctx->kp_pfpksk_bytes()));
+    if (!ctx->pfpksk) CU(cudaMalloc(&ctx->pfpksk, ctx->pfpksk_bytes()));
     ctx->keys_allocated = true;
     return TFA_OK;
 }
@@ -139,7 +140,8 @@ extern "C" int tfa_ctx_key_buffers(tfa_ctx *ctx, void **ptrs, size_t *bytes, int
     ptrs[0] = ctx->bsk_f; bytes[0] = ctx->bsk_f_bytes();
     ptrs[1] = ctx->kp_ksk; bytes[1] = ctx->kp_ksk_bytes();
     ptrs[2] = ctx->kp_pfpksk; bytes[2] = ctx->kp_pfpksk_bytes();
-    *count = 3;
+    ptrs[3] = ctx->pfpksk; bytes[3] = ctx->pfpksk_bytes();
+    *count = 4;
     return TFA_OK;
 }
 extern "C" int tfa_ctx_keys_ready(tfa_ctx *ctx) {
@@ -148,7 +150,8 @@ extern "C" int tfa_ctx_keys_ready(tfa_ctx *ctx) {
     return TFA_OK;
 }
 
-// standard-domain staging buffers for the two integer keys (freed again by prepare_keys_from_device)
+// standard-domain buffers of the two integer keys: the KSK one is staging only (freed again by
+// prepare_keys_from_device); the PFPKSK stays, it is the B operand of the tcgen05 PFKS kernel as it lies
 int alloc_key_staging(tfa_ctx *ctx) {
     if (!ctx->ksk) CU(cudaMalloc(&ctx->ksk, ctx->ksk_bytes()));
     if (!ctx->pfpksk) CU(cudaMalloc(&ctx->pfpksk, ctx->pfpksk_bytes()));
@@ -164,8 +167,8 @@ int prepare_keys_from_device(tfa_ctx *ctx, const u64 *bsk_std_dev) {
                                ctx->stream));
     ctx->launches += 2;
     CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->ksk); cudaFree(ctx->pfpksk);
-    ctx->ksk = nullptr; ctx->pfpksk = nullptr;
+    cudaFree(ctx->ksk);
+    ctx->ksk = nullptr;
     ctx->keys_ready = true;
     return TFA_OK;
 }
@@ -246,6 +249,13 @@ int dev_pfks(tfa_ctx *ctx, const u64 *in, int count, u64 *out, int out_stride) {
         CU(launch_imma_decompose(in, ctx->lw, ctx->big + 1, count, ctx->p.pfks_base_log, ctx->p.pfks_level, rows_pad, dl, dh, ctx->stream));
     }
     StageTimer t(ctx, ST_PFKS_GEMV);
+    static const bool force_imma = getenv("TFA_PFKS_IMMA") != nullptr;
+    if (!force_imma && limbs == 2 && ctx->pfpksk && tc5_pfks_supported(ctx->gsz, rows_pad)) {
+        // 5th-generation tensor cores, key consumed in its standard layout (tc5_kernels.cu)
+        CU(launch_tc5_pfks(dl, dh, rows_pad, ctx->pfpksk, kp1, ctx->pf_rows(), ctx->gsz, count, out, out_stride, ctx->stream));
+        ctx->launches += 1;
+        return TFA_OK;
+    }
     CU(launch_gemv_init(out, out_stride, kp1 * ctx->gsz, count, nullptr, 0, nullptr, 0, 0, 0, ctx->stream));
     ImmaGemvArgs g{};
     g.dl = dl; g.dh = dh; g.kp = ctx->kp_pfpksk; g.out = out; g.out_stride = out_stride; g.rows_pad = rows_pad;

@@ -68,6 +68,11 @@ cudaError_t launch_imma_decompose(const uint64_t *in, int in_stride, int nelem, 
                                   int8_t *dl, int8_t *dh, cudaStream_t s);
 cudaError_t launch_imma_gemv(const ImmaGemvArgs &a, int digit_limbs, cudaStream_t s);
 
+// tcgen05 PFKS (tc5_kernels.cu): key in its standard layout [nkeys][rows][ncols] u64
+bool tc5_pfks_supported(int ncols, int rows_pad);
+cudaError_t launch_tc5_pfks(const int8_t *dl, const int8_t *dh, int rows_pad, const uint64_t *key, int nkeys, int rows, int ncols, int count,
+                            uint64_t *out, int out_stride, cudaStream_t s);
+
 cudaError_t launch_pbs(int K, int G, int base_log, int levels, const PbsArgs &a, cudaStream_t s);
 cudaError_t launch_pbs_ws(int K, int G, int base_log, int levels, const PbsArgs &a, cudaStream_t s);
 cudaError_t launch_vp(int K, int G, int base_log, int levels, const VpArgs &a, cudaStream_t s);
