@@ -284,7 +284,8 @@ int dev_pbs(tfa_ctx *ctx, const u64 *in, int count, const u64 *lut, u64 in_scale
     const bool use_ws = ws_available && ctx->pbs_schedule != 1;
     if (timing && G == 3 && ctx->k == 4) {
         // debug aid: per-phase clock64() totals of block 0 (one thread per role)
-        uint64_t *d = nullptr, h[16] = {0};
+        uint64_t *d = nullptr;
+        static uint64_t h[16 + 3 * 512];
         CU(cudaMalloc(&d, sizeof(h)));
         CU(cudaMemsetAsync(d, 0, sizeof(h), ctx->stream));
         a.dbg = d;
@@ -299,6 +300,15 @@ int dev_pbs(tfa_ctx *ctx, const u64 *in, int count, const u64 *lut, u64 in_scale
         fprintf(stderr, "[pbs timing] cycles per CMux step (block 0):");
         for (int k = 0; k < 9; k++) fprintf(stderr, " %s=%.0f", use_ws ? nw[k] : nm[k], (double)h[k] / ctx->n);
         fprintf(stderr, "\n");
+        if (use_ws && getenv("TFA_PBS_TRACE")) {   // event times of steps 100..103: FFT group 0, FFT group 14, MAC thread 0
+            uint64_t t0 = ~0ull;
+            for (int k = 16; k < 16 + 3 * 512; k++) if (h[k] && h[k] < t0) t0 = h[k];
+            for (int sec = 0; sec < 3; sec++) {
+                fprintf(stderr, "[pbs trace] %s:", sec == 0 ? "fft_g0" : sec == 1 ? "fft_g14" : "mac");
+                for (int k = 0; k < 512 && h[16 + sec * 512 + k]; k++) fprintf(stderr, " %llu", (unsigned long long)(h[16 + sec * 512 + k] - t0));
+                fprintf(stderr, "\n");
+            }
+        }
         ctx->launches++;
         return TFA_OK;
     }

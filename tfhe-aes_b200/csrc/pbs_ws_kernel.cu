@@ -97,7 +97,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     long long tacc[6] = {0, 0, 0, 0, 0, 0};
     long long tlast = TIMING ? clock64() : 0;
-#define WT(k) do { if (TIMING) { const long long t_ = clock64(); tacc[(k) % 6] += t_ - tlast; tlast = t_; } } while (0)
+#define WT(k) do { if (TIMING) { const long long t_ = clock64(); tacc[(k) % 6] += t_ - tlast; tlast = t_; \
+                              if (trace_on && trace_idx < 512) a.dbg[16 + trace_sec * 512 + trace_idx++] = (uint64_t)t_; } } while (0)
+    int trace_sec = 0, trace_idx = 0;
+    bool trace_on = false;
     WsSmem<K, G> &sm = *reinterpret_cast<WsSmem<K, G> *>(smem_raw);
     const int tid = threadIdx.x;
     const int n = a.lwe_dim;
@@ -160,6 +163,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
             for (int i = 0; i < n; i++) {
                 // the mask element of the next step is fetched one step ahead (its latency hides behind a CMux)
                 const int rot_next = (i + 1 < n) ? ws_mod_switch_2n(a, my_ct, i + 1) : 0;
+                if (TIMING) { trace_on = blockIdx.x == 0 && (ftid == 0 || ftid == 224) && i >= 100 && i < 104; trace_sec = ftid == 0 ? 0 : 1; }
                 load_decompose_rot<BASE_LOG, LEVELS>(sm.acc[ct][r], lane, rot, v, st_re, st_im);
                 rot = rot_next;
                 WT(WT_F_DECOMP);
@@ -227,6 +231,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
         int q = 0;                                // next key row to consume
 #pragma unroll 1
         for (int i = 0; i < n; i++) {
+            if (TIMING) { trace_on = blockIdx.x == 0 && p == 0 && i >= 100 && i < 104; trace_sec = 2; }
 #pragma unroll
             for (int g = 0; g < G; g++)
 #pragma unroll
