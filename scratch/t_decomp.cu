@@ -18,7 +18,7 @@ static int check_torus() {
     const int n = 1 << 18;
     std::mt19937_64 g(9);
     std::vector<double> v(n);
-    for (int i = 0; i < n; i++) v[i] = ldexp((double)(int64_t)g() / 9223372036854775808.0, (int)(g() % 114));
+    for (int i = 0; i < n; i++) v[i] = ldexp((double)(int64_t)g() / 9223372036854775808.0, (int)(g() % 92));
     v[0] = 0.5; v[1] = -0.5; v[2] = 2147483648.0; v[3] = -2147483648.5; v[4] = 2147483647.5; v[5] = -0.0;
     double *dv; uint64_t *dout;
     cudaMalloc(&dv, n * 8); cudaMalloc(&dout, n * 8);

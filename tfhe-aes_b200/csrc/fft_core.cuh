@@ -128,37 +128,39 @@ HD void fft256_inv_pass2(cd (&v)[16], int lane, const cd *xb) {
 #pragma unroll
     for (int k1 = 0; k1 < 16; k1++) t[k1] = xb[xb_idx(lane, k1)];
     fft16<-1>(t);
+    // untwist by conj(phi^n1) with the 1/256 scale folded into the constants (a power of two: the products are
+    // the same doubles as scaling afterwards)
+    v[0] = cmk(t[rev4(0)].x * (1.0 / 256.0), t[rev4(0)].y * (1.0 / 256.0));
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) {
-        cd u = mul_w64<-1>(t[rev4(n1)], n1);
-        v[n1] = cmk(u.x * (1.0 / 256.0), u.y * (1.0 / 256.0));
+    for (int n1 = 1; n1 < 16; n1++) {
+        const cd x = t[rev4(n1)];
+        const double c = w64_cos(n1) * (1.0 / 256.0), s = -w64_sin(n1) * (1.0 / 256.0);
+        v[n1] = cmk(x.x * c - x.y * s, x.x * s + x.y * c);
     }
 }
 
 // round-to-nearest(-even) f64 -> u64 modulo 2^64 (SURVEY §9.6 "round to nearest, reduce mod 2^64"), valid for
-// |v| < 2^115 (the level-1 products of vertical packing reach ~2^83, worst case 2^89).  No conversion
-// instructions (FRND / F2I issue at 1/4 of the FP64 rate on B200, scratch/mb_xu.cu): with M = 1.5 * 2^52,
-//   q = v * 2^-64 + M,  w = v - (q - M) * 2^64     -> exact, |w| <= 2^63, w = v (mod 2^64)
-//   t = w * 2^-32 + M                              -> low word of t = h mod 2^32,  h = rint(w / 2^32)
-//   r = w - h * 2^32                               -> exact, |r| <= 2^31
-//   u = r + M                                      -> bits(u) - bits(M) = rint(r) as a signed 64-bit integer
-//   result = (h << 32) + rint(r) = rint(v)  (mod 2^64)
+// |v| < 2^93 (bootstrap products stay below 2^84, the level-1 products of vertical packing below 2^89).  No
+// conversion instructions (FRND / F2I issue at 1/4 of the FP64 rate on B200, scratch/mb_xu.cu) and four FP64
+// operations: with M = 1.5 * 2^52,
+//   t = v * 2^-42 + M      -> low word of t = h mod 2^32,  h = rint(v / 2^42)     (only h mod 2^22 is needed)
+//   r = v - h * 2^42       -> exact, |r| <= 2^41
+//   u = r + M              -> bits(u) - bits(M) = rint(r) as a signed 64-bit integer
+//   result = (h << 42) + rint(r) = rint(v)  (mod 2^64)
 HD uint64_t f64_to_torus(double v) {
     const double M = 6755399441055744.0;
-    const double q = fma(v, 1.0 / 18446744073709551616.0, M);
-    const double w = fma(-(q - M), 18446744073709551616.0, v);
-    const double t = fma(w, 1.0 / 4294967296.0, M);
+    const double t = fma(v, 1.0 / 4398046511104.0, M);
     const double h = t - M;
-    const double r = fma(-h, 4294967296.0, w);
+    const double r = fma(-h, 4398046511104.0, v);
     const double u = r + M;
 #ifdef __CUDA_ARCH__
     const uint32_t lo = (uint32_t)__double2loint(u);
-    const uint32_t hi = (uint32_t)__double2loint(t) + (uint32_t)__double2hiint(u) - 0x43380000u;
+    const uint32_t hi = ((uint32_t)__double2loint(t) << 10) + (uint32_t)__double2hiint(u) - 0x43380000u;
     return ((uint64_t)hi << 32) | lo;
 #else
     uint64_t bt, bu;
     __builtin_memcpy(&bt, &t, 8);
     __builtin_memcpy(&bu, &u, 8);
-    return (bt << 32) + (bu - 0x4338000000000000ull);
+    return (bt << 42) + (bu - 0x4338000000000000ull);
 #endif
 }

@@ -18,8 +18,8 @@
 // is re-balanced with setmaxnreg (144 / 112 per thread at G = 3).
 //
 // Bootstrap key: rows [col][p] of (K+1) x 4 KB, stored in consumption order, streamed L2 -> shared memory by
-// the TMA engine (cp.async.bulk, one lane per row) into a ring of K+1 slots (one level); BFULL[r] counts the
-// bytes of a row, BEMPTY[r] one arrival per MAC warp; the producer role rotates over the MAC warps and refills
+// the TMA engine (cp.async.bulk, one lane per row) into a ring of K+1 slots (one level); BFULL[0/1] count the
+// bytes of the first / second half of the rows of a level, BEMPTY[r] one arrival per MAC warp; the producer role rotates over the MAC warps and refills
 // the slot released one row earlier.
 // Hand-shake per row r (mbarriers in shared memory): RFULL[r] (one arrival per FFT group (ct, r), MAC threads
 // wait), REMPTY[r] (one arrival per MAC warp, the FFT lanes of row r wait before they overwrite their slot),
@@ -76,7 +76,7 @@ struct WsSmem {
     cd ring[K + 1][K + 1][POLY_M];       // one level of the Fourier bootstrap key: [row][col][p]
     uint64_t rfull[K + 1];
     uint64_t rempty[K + 1];
-    uint64_t bfull[K + 1];
+    uint64_t bfull[2];                   // key rows 0..BSPLIT-1 / BSPLIT..K of a level have landed
     uint64_t bempty[K + 1];
     uint64_t inv;
     uint64_t pad_;
@@ -111,6 +111,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
     constexpr unsigned ROW_BYTES = (unsigned)(ROW_ELEMS * sizeof(cd));
     const int nrows = n * ROWS;
     // register split (per thread, 8 + 8 warps, 128 on average): the MAC role holds G*(K+1) complex accumulators
+    // The key ring is watched by two barriers per level (a try_wait costs ~95 cycles on the barrier unit even when
+    // the phase is long complete, and they serialise): rows [0, BSPLIT) are waited for when the level starts, rows
+    // [BSPLIT, K] just before row BSPLIT (the slot of the last row is only refilled at row 0 of the next level).
+    constexpr int BSPLIT = (K + 2) / 2;
     constexpr int MAC_REGS = G >= 3 ? 112 : (G == 2 ? 96 : 72);
 
     // ---- prologue (all 512 threads) ---------------------------------------------------------------
@@ -119,9 +123,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
         for (int r = 0; r <= K; r++) {
             ws_mbar_init(&sm.rfull[r], G);
             ws_mbar_init(&sm.rempty[r], WS_MAC_WARPS);
-            ws_mbar_init(&sm.bfull[r], 1);
             ws_mbar_init(&sm.bempty[r], WS_MAC_WARPS);
         }
+        ws_mbar_init(&sm.bfull[0], BSPLIT);
+        ws_mbar_init(&sm.bfull[1], K + 1 - BSPLIT);
         ws_mbar_init(&sm.inv, WS_MAC_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
         const int ct = active ? gid % G : 0, r = active ? gid / G : 0;
         // Both 16-lane groups of a warp execute ONE instruction stream (a diverged half-warp would pay a full
         // issue slot and a full FP64 pipe pass for 16 lanes): waits are made warp-uniform by waiting for the
-        // rows of both groups; an idle group (gid >= G*(K+1)) runs along with its stores predicated off.
+        // later row of the two groups; an idle group (gid >= G*(K+1)) runs along with its stores predicated off.
         const int gid_a = (ftid >> 5) * 2, gid_b = gid_a + 1;
         const int r_a = gid_a / G;
         const int r_b = (gid_b < G * (K + 1)) ? gid_b / G : r_a;
@@ -174,7 +179,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
                     // occupant of the slot (rows of the previous production)
                     fft256_fwd_pass1_compute(v, lane, sm.tw);
                     WT(WT_F_PASS1);
-                    if (produced > 0) ws_mbar_wait2(&sm.rempty[r_a], (produced - 1) & 1, &sm.rempty[r_b], (produced - 1) & 1);
+                    // (every MAC warp releases the rows of a level in order, so the release of row r_b >= r_a implies r_a's)
+                    if (produced > 0) ws_mbar_wait(&sm.rempty[r_b], (produced - 1) & 1);
                     WT(WT_F_WAIT_EMPTY);
                     if (active) fft256_fwd_pass1_store(v, lane, slot);
                     __syncwarp();
@@ -221,8 +227,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
         const int mwarp = p >> 5, mlane = p & 31;
         auto produce = [&](int q) {               // fetch key row q into slot q % RING (the caller knows it is free)
             const int s = q % RING;
-            ws_mbar_arrive_expect_tx(&sm.bfull[s], ROW_BYTES);
-            ws_bulk_copy_g2s(&sm.ring[s][0][0], a.bsk + (size_t)q * ROW_ELEMS, ROW_BYTES, &sm.bfull[s]);
+            uint64_t *bar = &sm.bfull[s < BSPLIT ? 0 : 1];
+            ws_mbar_arrive_expect_tx(bar, ROW_BYTES);
+            ws_bulk_copy_g2s(&sm.ring[s][0][0], a.bsk + (size_t)q * ROW_ELEMS, ROW_BYTES, bar);
         };
         if (p == 0)
             for (int q = 0; q < RING; q++) produce(q);   // nrows >= RING always
@@ -241,7 +248,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
                 const unsigned parity = level_count & 1;
 #pragma unroll
                 for (int r = 0; r <= K; r++, q++) {
-                    ws_mbar_wait2(&sm.bfull[r], parity, &sm.rfull[r], parity);
+                    if (r == 0) ws_mbar_wait2(&sm.bfull[0], parity, &sm.rfull[r], parity);
+                    else if (r == BSPLIT) ws_mbar_wait2(&sm.bfull[1], parity, &sm.rfull[r], parity);
+                    else ws_mbar_wait(&sm.rfull[r], parity);
                     WT(WT_M_WAIT);
                     cd x[G];
 #pragma unroll
