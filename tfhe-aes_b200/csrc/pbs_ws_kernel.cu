@@ -142,10 +142,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
     // Role by warp index: the MAC role takes warps 0-7 and the FFT role warps 8-15.  The FFT warps are the critical
     // path (they carry 64 % of the FP64 work plus all integer work), and the issue arbiter favours the higher
     // warp ids when several warps of a scheduler are eligible.
-    if (tid >= WS_THREADS - WS_FFT_THREADS) {
+#ifndef WS_FFT_HIGH
+#define WS_FFT_HIGH 1
+#endif
+    if (WS_FFT_HIGH ? (tid >= WS_THREADS - WS_FFT_THREADS) : (tid < WS_FFT_THREADS)) {
         // ================================ FFT warps ================================================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(256 - MAC_REGS));
-        const int ftid = tid - (WS_THREADS - WS_FFT_THREADS);
+        const int ftid = WS_FFT_HIGH ? tid - (WS_THREADS - WS_FFT_THREADS) : tid;
         const int gid = ftid >> 4, lane = ftid & 15;
         const bool active = gid < G * (K + 1);
         // group -> polynomial: row-major (r = gid / G, ct = gid % G), so that the two groups of a warp own the same
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
     } else {
         // ================================ MAC warps ================================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MAC_REGS));
-        const int p = tid;
+        const int p = WS_FFT_HIGH ? tid : tid - WS_FFT_THREADS;
         const int mwarp = p >> 5, mlane = p & 31;
         auto produce = [&](int q) {               // fetch key row q into slot q % RING (the caller knows it is free)
             const int s = q % RING;
