@@ -345,9 +345,63 @@ static int add_scalar_nolock(tfa_ctx *ctx, u64 *state, const u64 *ctr_dev, int n
     CU(cudaMemcpyAsync(state, ns, (size_t)nblk * 16 * bw * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     return TFA_OK;
 }
+// Counter add of the CTR loop (main.rs:59-60: state = encrypted_iv.clone(); add_scalar(&mut state, i)) for nblk counters
+// at once.  Every block starts from the SAME encrypted IV, so the 8 state bits of each stage are the same ciphertexts for
+// all blocks: they are circuit-bootstrapped once (128 bits for the whole call) and their GGSWs are shared by the
+// vertical packings of all blocks; per block and stage only the carry bit (block 8 of the 9-block radix of
+// server.rs:216-222) goes through its own circuit bootstrap.  Per block 15 instead of 143 bootstraps; the outputs are the
+// same functions of the same inputs (the LUTs, the selector order and the carry chain are those of add_scalar_nolock).
+static int add_scalar_from_iv_nolock(tfa_ctx *ctx, const u64 *iv_ct, const u64 *ctr_dev, int nblk, u64 *states) {
+    if (nblocks_per_byte(ctx) != 8) return ctx->fail(TFA_ERR_UNSUPPORTED, "add_scalar needs 1-bit blocks (client.rs:53-54)");
+    const size_t bw = ctx->byte_words();
+    const int lw = ctx->lw, np = ctx->n + 1;
+    const size_t ggsw_words = (size_t)ctx->p.cbs_level * (ctx->k + 1) * ctx->gsz;
+    // (1) the 128 IV bits: extract (keyswitch), circuit bootstrap, Fourier — bit t of byte b at index 8*b + t
+    WSB(iv_bits, u64, (size_t)128 * np);
+    WSB(iv_ggsw_std, u64, (size_t)128 * ggsw_words);
+    WSB(iv_ggsw_f, double2, (size_t)128 * ggsw_words / 2);
+    const int delta_log = 63;
+    {
+        const size_t mark0 = ctx->ws_off;
+        RC(dev_extract_bits(ctx, iv_ct, 128, delta_log, 1, iv_bits));
+        RC(dev_circuit_bootstrap(ctx, iv_bits, 128, iv_ggsw_std));
+        RC(dev_fourier(ctx, iv_ggsw_std, (long)128 * ctx->p.cbs_level * (ctx->k + 1) * (ctx->k + 1), ctx->p.cbs_level, iv_ggsw_f));
+        ctx->ws_off = mark0;
+    }
+    WSB(out9, u64, (size_t)nblk * 9 * lw);
+    WSB(carry, u64, (size_t)nblk * lw);
+    WSB(carry_bits, u64, (size_t)nblk * np);
+    WSB(carry_ggsw_std, u64, (size_t)nblk * ggsw_words);
+    WSB(carry_ggsw_f, double2, (size_t)nblk * ggsw_words / 2);
+    WSB(luts, u64, (size_t)nblk * 9 * 512);
+    const size_t mark = ctx->ws_off;
+    for (int stage = 0; stage < 16; stage++) {
+        ctx->ws_off = mark;
+        const int index = 15 - stage, nbits = stage == 0 ? 8 : 9;
+        CU(launch_add_scalar_luts(ctr_dev, nblk, index, nbits, luts, ctx->stream));
+        ctx->launches++;
+        if (stage > 0) {
+            // the carry of the previous stage (output 8) is the 9th selector bit of this one
+            std::vector<SumEntry> v;
+            for (int b = 0; b < nblk; b++) v.push_back(entry(carry + (size_t)b * lw, {out9 + ((size_t)b * 9 + 8) * lw}));
+            RC(dev_lwe_sum(ctx, v, lw));
+            RC(dev_extract_bits(ctx, carry, nblk, delta_log, 1, carry_bits));
+            RC(dev_circuit_bootstrap(ctx, carry_bits, nblk, carry_ggsw_std));
+            RC(dev_fourier(ctx, carry_ggsw_std, (long)nblk * ctx->p.cbs_level * (ctx->k + 1) * (ctx->k + 1), ctx->p.cbs_level, carry_ggsw_f));
+        }
+        // the 8 sum bits and the carry bit the reference reads back (server.rs:255-263)
+        RC(dev_vertical_packing(ctx, carry_ggsw_f, nblk, nbits, luts, (size_t)9 * 512, 512, 9, 512, out9,
+                                iv_ggsw_f + (size_t)index * 8 * ggsw_words / 2, 8));
+        std::vector<SumEntry> v;
+        for (int b = 0; b < nblk; b++) for (int j = 0; j < 8; j++)
+            v.push_back(entry(states + ((size_t)b * 16 + index) * bw + (size_t)j * lw, {out9 + ((size_t)b * 9 + j) * lw}));
+        RC(dev_lwe_sum(ctx, v, lw));
+    }
+    return TFA_OK;
+}
 static size_t add_scalar_scratch(const tfa_ctx *ctx, int nblk) {
-    return many_wopbs_scratch(ctx, nblk, 9, 9, 512) + (size_t)nblk * (16 * ctx->byte_words() + 18 * ctx->lw + 9 * 512) * 8 +
-           (size_t)nblk * 32 * sizeof(SumEntry) + (1 << 20);
+    return many_wopbs_scratch(ctx, nblk, 9, 9, 512) + many_wopbs_scratch(ctx, 16, 8, 8, 512) +
+           (size_t)nblk * (16 * ctx->byte_words() + 20 * ctx->lw + 9 * 512) * 8 + (size_t)nblk * 32 * sizeof(SumEntry) + (1 << 20);
 }
 
 // ---- device-pointer entry points -----------------------------------------------------------------
@@ -396,9 +450,14 @@ static int aes_ctr_nolock(tfa_ctx *ctx, const u64 *rk, const u64 *iv_ct, u64 fir
     }
     WSB(d_ctr, u64, ctr.size());
     CU(cudaMemcpyAsync(d_ctr, ctr.data(), ctr.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    for (int b = 0; b < nblk; b++) CU(cudaMemcpyAsync(out + (size_t)b * sw, iv_ct, sw * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     const size_t mark = ctx->ws_off;
-    RC(add_scalar_nolock(ctx, out, d_ctr, nblk));
+    static const bool per_block = getenv("TFA_CTR_PER_BLOCK_ADD") != nullptr;   // the reference's schedule, for comparison
+    if (per_block) {
+        for (int b = 0; b < nblk; b++) CU(cudaMemcpyAsync(out + (size_t)b * sw, iv_ct, sw * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        RC(add_scalar_nolock(ctx, out, d_ctr, nblk));
+    } else {
+        RC(add_scalar_from_iv_nolock(ctx, iv_ct, d_ctr, nblk, out));
+    }
     ctx->ws_off = mark;
     return aes_encrypt_nolock(ctx, rk, out, nblk);
 }

@@ -25,8 +25,10 @@ struct VpArgs {
     uint64_t *out;            // [njobs][nouts][k*N+1]
     size_t lut_job_stride;
     size_t lut_out_stride;
-    int nbits;                // GGSWs per job
+    int nbits;                // selector bits (GGSWs) per job, of which the first nshared come from ggsw_shared
     int nrot;                 // GGSWs consumed by the blind rotation (bits 0..nrot-1)
+    const double2 *ggsw_shared;  // [nshared][level][row][col][p]: GGSWs common to all jobs (bits 0..nshared-1), or nullptr
+    int nshared;              // ggsw_f then holds nbits - nshared GGSWs per job
     int nouts;
     int njobs;
 };
