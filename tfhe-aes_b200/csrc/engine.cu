@@ -132,6 +132,7 @@ extern "C" int tfa_ctx_alloc_keys(tfa_ctx *ctx) {
     CU(cudaMalloc(&ctx->kp_ksk, ctx->kp_ksk_bytes()));
     CU(cudaMalloc(&ctx->kp_pfpksk, ctx->kp_pfpksk_bytes()));
     if (!ctx->pfpksk) CU(cudaMalloc(&ctx->pfpksk, ctx->pfpksk_bytes()));
+    if (!ctx->ksk) CU(cudaMalloc(&ctx->ksk, ctx->ksk_bytes()));
     ctx->keys_allocated = true;
     return TFA_OK;
 }
@@ -141,7 +142,8 @@ extern "C" int tfa_ctx_key_buffers(tfa_ctx *ctx, void **ptrs, size_t *bytes, int
     ptrs[1] = ctx->kp_ksk; bytes[1] = ctx->kp_ksk_bytes();
     ptrs[2] = ctx->kp_pfpksk; bytes[2] = ctx->kp_pfpksk_bytes();
     ptrs[3] = ctx->pfpksk; bytes[3] = ctx->pfpksk_bytes();
-    *count = 4;
+    ptrs[4] = ctx->ksk; bytes[4] = ctx->ksk_bytes();
+    *count = 5;
     return TFA_OK;
 }
 extern "C" int tfa_ctx_keys_ready(tfa_ctx *ctx) {
@@ -150,8 +152,8 @@ extern "C" int tfa_ctx_keys_ready(tfa_ctx *ctx) {
     return TFA_OK;
 }
 
-// standard-domain buffers of the two integer keys: the KSK one is staging only (freed again by
-// prepare_keys_from_device); the PFPKSK stays, it is the B operand of the tcgen05 PFKS kernel as it lies
+// standard-domain buffers of the two integer keys (KSK with rows padded to ks_cols_pad words): they stay, they are the
+// B operands of the tcgen05 keyswitch kernels exactly as they lie
 int alloc_key_staging(tfa_ctx *ctx) {
     if (!ctx->ksk) CU(cudaMalloc(&ctx->ksk, ctx->ksk_bytes()));
     if (!ctx->pfpksk) CU(cudaMalloc(&ctx->pfpksk, ctx->pfpksk_bytes()));
@@ -167,8 +169,6 @@ int prepare_keys_from_device(tfa_ctx *ctx, const u64 *bsk_std_dev) {
                                ctx->stream));
     ctx->launches += 2;
     CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->ksk);
-    ctx->ksk = nullptr;
     ctx->keys_ready = true;
     return TFA_OK;
 }
@@ -224,6 +224,13 @@ int dev_keyswitch(tfa_ctx *ctx, const u64 *in, int count, u64 *out) {
         CU(launch_imma_decompose(in, ctx->lw, ctx->big, count, ctx->p.ks_base_log, ctx->p.ks_level, rows_pad, dl, dh, ctx->stream));
     }
     StageTimer t(ctx, ST_KS_GEMV);
+    static const bool force_imma = getenv("TFA_KS_IMMA") != nullptr;
+    if (!force_imma && limbs == 1 && ctx->ksk && tc5_ks_supported(np, ctx->ks_cols_pad, rows_pad)) {
+        // 5th-generation tensor cores, key consumed in its standard layout (tc5_kernels.cu)
+        CU(launch_tc5_keyswitch(dl, rows_pad, ctx->ksk, ctx->ks_rows(), np, ctx->ks_cols_pad, count, in, ctx->lw, ctx->big, out, np, ctx->stream));
+        ctx->launches += 1;
+        return TFA_OK;
+    }
     CU(launch_gemv_init(out, np, np, count, nullptr, 0, in, ctx->lw, ctx->big, ctx->n, ctx->stream));
     ImmaGemvArgs g{};
     g.dl = dl; g.dh = dh; g.kp = ctx->kp_ksk; g.out = out; g.out_stride = np; g.rows_pad = rows_pad;

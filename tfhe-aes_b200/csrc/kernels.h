@@ -74,6 +74,9 @@ cudaError_t launch_imma_gemv(const ImmaGemvArgs &a, int digit_limbs, cudaStream_
 bool tc5_pfks_supported(int ncols, int rows_pad);
 cudaError_t launch_tc5_pfks(const int8_t *dl, const int8_t *dh, int rows_pad, const uint64_t *key, int nkeys, int rows, int ncols, int count,
                             uint64_t *out, int out_stride, cudaStream_t s);
+bool tc5_ks_supported(int ncols, int key_pitch_cols, int rows_pad);
+cudaError_t launch_tc5_keyswitch(const int8_t *dl, int rows_pad, const uint64_t *key, int rows, int ncols, int key_pitch_cols, int count,
+                                 const uint64_t *in, int in_stride, int body_index, uint64_t *out, int out_stride, cudaStream_t s);
 
 cudaError_t launch_pbs(int K, int G, int base_log, int levels, const PbsArgs &a, cudaStream_t s);
 cudaError_t launch_pbs_ws(int K, int G, int base_log, int levels, const PbsArgs &a, cudaStream_t s);

@@ -31,10 +31,11 @@
 #define T5_M 128                 // bits per CTA
 #define T5_NB 256                // byte-columns per CTA (32 u64 columns x 8 limbs)
 #define T5_KS 128                // key rows per pipeline stage
-#define T5_STAGES 3
 #define T5_THREADS 192
 #define T5_TILE_BYTES (T5_M * 128)                 // one 128-row x 128-byte operand block = 16 KB
-#define T5_STAGE_BYTES (4 * T5_TILE_BYTES)         // A_lo, A_hi, B block 0, B block 1
+// DL = digit limbs (2: PFKS, digits up to 2^11; 1: LWE keyswitch, |digit| <= 2).  Stage = DL A blocks + 2 B blocks.
+#define T5_STAGE_BYTES(DL) (((DL) + 2) * T5_TILE_BYTES)
+#define T5_STAGES(DL) ((DL) == 2 ? 3 : 4)
 
 __device__ __forceinline__ unsigned t5_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void t5_mbar_init(uint64_t *bar, unsigned count) {
@@ -76,6 +77,8 @@ __device__ __forceinline__ void t5_commit(uint64_t *bar) {
 }
 
 struct Tc5Args {
+    const uint64_t *body_src; // keyswitch only: [count][body_stride] input LWEs, word body_index is added to column body_col
+    int body_stride, body_index, body_col;
     uint64_t *out;            // [count][out_stride]; the product is written negated (no read-modify-write)
     int out_stride;
     int count;                // bits
@@ -88,14 +91,17 @@ struct Tc5Args {
 // instruction descriptor: D = s32, A = s8 (K-major), B = u8 (MN-major), M = 128, N = 256, dense, no saturation
 #define T5_IDESC ((2u << 4) | (1u << 7) | (0u << 10) | (0u << 15) | (1u << 16) | ((T5_NB >> 3) << 17) | ((T5_M >> 4) << 24))
 
-__global__ void __launch_bounds__(T5_THREADS, 1) tc5_pfks_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_constant__ CUtensorMap map_dh,
-                                                                 const __grid_constant__ CUtensorMap map_key, Tc5Args a) {
+template <int DL>
+__global__ void __launch_bounds__(T5_THREADS, 1) tc5_keyswitch_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_constant__ CUtensorMap map_dh,
+                                                                      const __grid_constant__ CUtensorMap map_key, Tc5Args a) {
+    constexpr int STAGES = T5_STAGES(DL);
+    constexpr unsigned STAGE_BYTES = T5_STAGE_BYTES(DL);
     extern __shared__ __align__(1024) unsigned char t5_smem_raw[];
-    // [T5_STAGES][T5_STAGE_BYTES]; the swizzled operand blocks need 1 KB alignment in the shared address space
+    // [STAGES][STAGE_BYTES]; the swizzled operand blocks need 1 KB alignment in the shared address space
     unsigned char *stages = t5_smem_raw + ((1024u - (t5_smem(t5_smem_raw) & 1023u)) & 1023u);
-    uint64_t *full = reinterpret_cast<uint64_t *>(stages + T5_STAGES * T5_STAGE_BYTES);         // [T5_STAGES]
-    uint64_t *empty = full + T5_STAGES;                                          // [T5_STAGES]
-    uint64_t *tmem_full = empty + T5_STAGES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(stages + STAGES * STAGE_BYTES);         // [STAGES]
+    uint64_t *empty = full + STAGES;                                          // [STAGES]
+    uint64_t *tmem_full = empty + STAGES;
     unsigned *tmem_ptr = reinterpret_cast<unsigned *>(tmem_full + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * T5_M;
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) tc5_pfks_kernel(const __grid_co
     const int row0 = keyi * a.rows;                                              // first key row of this key in the key tensor
 
     if (tid == 0) {
-        for (int s = 0; s < T5_STAGES; s++) { t5_mbar_init(&full[s], 1); t5_mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; s++) { t5_mbar_init(&full[s], 1); t5_mbar_init(&empty[s], 1); }
         t5_mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -122,33 +128,32 @@ __global__ void __launch_bounds__(T5_THREADS, 1) tc5_pfks_kernel(const __grid_co
         // ---------------- TMA producer ----------------
         if (lane == 0) {
             for (int kc = 0; kc < a.nk; kc++) {
-                const int s = kc % T5_STAGES;
-                if (kc >= T5_STAGES) t5_mbar_wait(&empty[s], ((kc / T5_STAGES) - 1) & 1);
-                unsigned char *st = stages + (size_t)s * T5_STAGE_BYTES;
-                t5_mbar_expect_tx(&full[s], T5_STAGE_BYTES);
-                t5_tma_load_2d(st, &map_dl, kc * T5_KS, m0, &full[s]);                                   // A_lo: [bit][128 rows]
-                t5_tma_load_2d(st + T5_TILE_BYTES, &map_dh, kc * T5_KS, m0, &full[s]);                   // A_hi
-                t5_tma_load_2d(st + 2 * T5_TILE_BYTES, &map_key, nb0, row0 + kc * T5_KS, &full[s]);        // B bytes nb0 .. +127
-                t5_tma_load_2d(st + 3 * T5_TILE_BYTES, &map_key, nb0 + 128, row0 + kc * T5_KS, &full[s]);  // B bytes nb0+128 ..
+                const int s = kc % STAGES;
+                if (kc >= STAGES) t5_mbar_wait(&empty[s], ((kc / STAGES) - 1) & 1);
+                unsigned char *st = stages + (size_t)s * STAGE_BYTES;
+                t5_mbar_expect_tx(&full[s], STAGE_BYTES);
+                t5_tma_load_2d(st, &map_dl, kc * T5_KS, m0, &full[s]);                                          // A_lo: [bit][128 rows]
+                if (DL == 2) t5_tma_load_2d(st + T5_TILE_BYTES, &map_dh, kc * T5_KS, m0, &full[s]);             // A_hi
+                t5_tma_load_2d(st + DL * T5_TILE_BYTES, &map_key, nb0, row0 + kc * T5_KS, &full[s]);              // B bytes nb0 .. +127
+                t5_tma_load_2d(st + (DL + 1) * T5_TILE_BYTES, &map_key, nb0 + 128, row0 + kc * T5_KS, &full[s]);  // B bytes nb0+128 ..
             }
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             for (int kc = 0; kc < a.nk; kc++) {
-                const int s = kc % T5_STAGES;
-                t5_mbar_wait(&full[s], (kc / T5_STAGES) & 1);
+                const int s = kc % STAGES;
+                t5_mbar_wait(&full[s], (kc / STAGES) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned st = t5_smem(stages + (size_t)s * T5_STAGE_BYTES);
+                const unsigned st = t5_smem(stages + (size_t)s * STAGE_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < T5_KS / 32; ks++) {
                     // K-major A: one MMA consumes 32 bytes of every 128-byte row; MN-major B: 32 rows of 128 bytes
                     const uint64_t da_lo = t5_desc(st + ks * 32, 16, 1024);
-                    const uint64_t da_hi = t5_desc(st + T5_TILE_BYTES + ks * 32, 16, 1024);
-                    const uint64_t db = t5_desc(st + 2 * T5_TILE_BYTES + ks * 32 * 128, T5_TILE_BYTES, 1024);
+                    const uint64_t db = t5_desc(st + DL * T5_TILE_BYTES + ks * 32 * 128, T5_TILE_BYTES, 1024);
                     const unsigned acc = (kc | ks) != 0;
                     t5_mma_i8(tmem_base, da_lo, db, T5_IDESC, acc);
-                    t5_mma_i8(tmem_base + T5_NB, da_hi, db, T5_IDESC, acc);
+                    if (DL == 2) t5_mma_i8(tmem_base + T5_NB, t5_desc(st + T5_TILE_BYTES + ks * 32, 16, 1024), db, T5_IDESC, acc);
                 }
                 t5_commit(&empty[s]);            // the stage may be refilled once these MMAs have read it
             }
@@ -161,7 +166,9 @@ __global__ void __launch_bounds__(T5_THREADS, 1) tc5_pfks_kernel(const __grid_co
         const int quarter = warp & 3;                                    // TMEM lanes 32*quarter .. +31 are this warp's
         const int bit = m0 + quarter * 32 + lane;
         const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16);
-        uint64_t *orow = a.out + (size_t)min(bit, a.count - 1) * a.out_stride + (size_t)keyi * a.ncols + nb0 / 8;
+        const int bitc = min(bit, a.count - 1);
+        uint64_t *orow = a.out + (size_t)bitc * a.out_stride + (size_t)keyi * a.ncols + nb0 / 8;
+        const uint64_t body = a.body_src ? a.body_src[(size_t)bitc * a.body_stride + a.body_index] : 0;
 #pragma unroll 1
         for (int c = 0; c < T5_NB / 16; c++) {                           // 16 byte-columns = 2 u64 outputs per step
             unsigned lo[16], hi[16];
@@ -169,10 +176,15 @@ __global__ void __launch_bounds__(T5_THREADS, 1) tc5_pfks_kernel(const __grid_co
                          : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]), "=r"(lo[4]), "=r"(lo[5]), "=r"(lo[6]), "=r"(lo[7]), "=r"(lo[8]),
                            "=r"(lo[9]), "=r"(lo[10]), "=r"(lo[11]), "=r"(lo[12]), "=r"(lo[13]), "=r"(lo[14]), "=r"(lo[15])
                          : "r"(taddr + c * 16));
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                         : "=r"(hi[0]), "=r"(hi[1]), "=r"(hi[2]), "=r"(hi[3]), "=r"(hi[4]), "=r"(hi[5]), "=r"(hi[6]), "=r"(hi[7]), "=r"(hi[8]),
-                           "=r"(hi[9]), "=r"(hi[10]), "=r"(hi[11]), "=r"(hi[12]), "=r"(hi[13]), "=r"(hi[14]), "=r"(hi[15])
-                         : "r"(taddr + T5_NB + c * 16));
+            if (DL == 2) {
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(hi[0]), "=r"(hi[1]), "=r"(hi[2]), "=r"(hi[3]), "=r"(hi[4]), "=r"(hi[5]), "=r"(hi[6]), "=r"(hi[7]), "=r"(hi[8]),
+                               "=r"(hi[9]), "=r"(hi[10]), "=r"(hi[11]), "=r"(hi[12]), "=r"(hi[13]), "=r"(hi[14]), "=r"(hi[15])
+                             : "r"(taddr + T5_NB + c * 16));
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; e++) hi[e] = 0;
+            }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             uint64_t v[2];
 #pragma unroll
@@ -183,9 +195,11 @@ __global__ void __launch_bounds__(T5_THREADS, 1) tc5_pfks_kernel(const __grid_co
                     const int64_t p = (int64_t)(int)lo[8 * o + b] + (int64_t)(int)hi[8 * o + b] * 128;
                     acc += (uint64_t)p << (8 * b);
                 }
-                v[o] = (uint64_t)0 - acc;
+                const int col = nb0 / 8 + 2 * c + o;
+                v[o] = ((a.body_src && col == a.body_col) ? body : (uint64_t)0) - acc;
             }
-            if (bit < a.count) *reinterpret_cast<ulonglong2 *>(orow + 2 * c) = make_ulonglong2(v[0], v[1]);
+            // (ncols is even and tiles start at multiples of 32 columns, so a pair is either all inside or all outside)
+            if (bit < a.count && nb0 / 8 + 2 * c < a.ncols) *reinterpret_cast<ulonglong2 *>(orow + 2 * c) = make_ulonglong2(v[0], v[1]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -221,6 +235,20 @@ static bool t5_make_map(CUtensorMap *m, const void *base, uint64_t inner_bytes, 
 }
 
 bool tc5_pfks_supported(int ncols, int rows_pad) { return (ncols * 8) % T5_NB == 0 && rows_pad % 16 == 0; }
+bool tc5_ks_supported(int ncols, int key_pitch_cols, int rows_pad) { return ncols % 2 == 0 && key_pitch_cols % 2 == 0 && rows_pad % 16 == 0; }
+
+template <int DL>
+static cudaError_t t5_launch(const CUtensorMap &map_dl, const CUtensorMap &map_dh, const CUtensorMap &map_key, const Tc5Args &a, dim3 grid, cudaStream_t s) {
+    const size_t smem = (size_t)T5_STAGES(DL) * T5_STAGE_BYTES(DL) + 1024 + 128;   // + alignment slack + barriers
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc5_keyswitch_kernel<DL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    tc5_keyswitch_kernel<DL><<<grid, T5_THREADS, smem, s>>>(map_dl, map_dh, map_key, a);
+    return cudaGetLastError();
+}
 
 // out[bit][key*ncols + col] = - sum_row (dl + 128 dh)[bit][row] * key[key][row][col];  dl/dh [count][rows_pad] (zero padded rows)
 cudaError_t launch_tc5_pfks(const int8_t *dl, const int8_t *dh, int rows_pad, const uint64_t *key, int nkeys, int rows, int ncols, int count,
@@ -235,14 +263,22 @@ cudaError_t launch_tc5_pfks(const int8_t *dl, const int8_t *dh, int rows_pad, co
     a.out = out; a.out_stride = out_stride; a.count = count; a.rows = rows; a.ncols = ncols;
     a.ntiles_per_key = ncols * 8 / T5_NB;
     a.nk = (rows + T5_KS - 1) / T5_KS;
-    const size_t smem = (size_t)T5_STAGES * T5_STAGE_BYTES + 1024 + 128;   // + alignment slack + barriers
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc5_pfks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    dim3 grid((count + T5_M - 1) / T5_M, a.ntiles_per_key * nkeys);
-    tc5_pfks_kernel<<<grid, T5_THREADS, smem, s>>>(map_dl, map_dh, map_key, a);
-    return cudaGetLastError();
+    return t5_launch<2>(map_dl, map_dh, map_key, a, dim3((count + T5_M - 1) / T5_M, a.ntiles_per_key * nkeys), s);
+}
+
+// LWE keyswitch: out[bit][col] = (col == body_col ? in[bit][body_index] : 0) - sum_row dl[bit][row] * key[row][col];
+// key [rows][key_pitch_cols] u64 (columns >= ncols are padding), one digit limb (|digit| <= 64)
+cudaError_t launch_tc5_keyswitch(const int8_t *dl, int rows_pad, const uint64_t *key, int rows, int ncols, int key_pitch_cols, int count,
+                                 const uint64_t *in, int in_stride, int body_index, uint64_t *out, int out_stride, cudaStream_t s) {
+    if (!tc5_ks_supported(ncols, key_pitch_cols, rows_pad)) return cudaErrorInvalidValue;
+    CUtensorMap map_dl, map_key;
+    if (!t5_make_map(&map_dl, dl, (uint64_t)rows_pad, (uint64_t)count, (uint64_t)rows_pad) ||
+        !t5_make_map(&map_key, key, (uint64_t)key_pitch_cols * 8, (uint64_t)rows, (uint64_t)key_pitch_cols * 8))
+        return cudaErrorInvalidValue;
+    Tc5Args a{};
+    a.body_src = in; a.body_stride = in_stride; a.body_index = body_index; a.body_col = ncols - 1;
+    a.out = out; a.out_stride = out_stride; a.count = count; a.rows = rows; a.ncols = ncols;
+    a.ntiles_per_key = (ncols * 8 + T5_NB - 1) / T5_NB;
+    a.nk = (rows + T5_KS - 1) / T5_KS;
+    return t5_launch<1>(map_dl, map_dl, map_key, a, dim3((count + T5_M - 1) / T5_M, a.ntiles_per_key), s);
 }
