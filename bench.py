@@ -36,6 +36,7 @@ def pbs_per_block(blocks):       # batched tfa_aes_ctr: IV bits bootstrapped onc
 
 
 BSK_BYTES = 342_528_000
+NCU_DRAM_BYTES_PER_WAVE = 350_468_864   # ncu --set full, pbs_ws_kernel<4,3,8,5>, 148 CTAs x 3 ciphertexts (profiles/r1_pbs_ws_kernel_ncu.txt)
 METRIC = "aes128_ctr_blocks_per_s"
 UNIT = "blocks/s"
 
@@ -368,7 +369,8 @@ def run_gpu(args):
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": {"bound": "fp64", "kernel": "pbs_ws_kernel<4,3,8,5>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
-                         "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 figure)", "traffic": None,
+                         "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 figure)", "traffic": NCU_DRAM_BYTES_PER_WAVE * -(-count // 444),
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one 444-PBS wave (profiles/r1_pbs_ws_kernel_ncu.txt: 346.2 + 4.2 MB) x waves in this launch; algorithmic = 342.5 MB of key per wave",
                          "launch_ms": pbs_ms, "pbs_per_launch": count, "flop_per_pbs": PBS_FLOP,
                          "bsk_hbm_gbs": BSK_BYTES * -(-count // (3 * 148)) / (pbs_ms * 1e-3) * 1e-9, "hbm_peak_gbs": hbm,
                          "note": "the key (342.5 MB) is read from HBM once per wave of 444 PBS and served from L2 to the other CTAs"},
