@@ -391,7 +391,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--blocks-per-gpu", type=int, default=48)
+    ap.add_argument("--blocks-per-gpu", type=int, default=148)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--iv", type=int, default=0)

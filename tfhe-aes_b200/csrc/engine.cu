@@ -258,9 +258,17 @@ int dev_pfks(tfa_ctx *ctx, const u64 *in, int count, u64 *out, int out_stride) {
     StageTimer t(ctx, ST_PFKS_GEMV);
     static const bool force_imma = getenv("TFA_PFKS_IMMA") != nullptr;
     if (!force_imma && limbs == 2 && ctx->pfpksk && tc5_pfks_supported(ctx->gsz, rows_pad)) {
-        // 5th-generation tensor cores, key consumed in its standard layout (tc5_kernels.cu)
-        CU(launch_tc5_pfks(dl, dh, rows_pad, ctx->pfpksk, kp1, ctx->pf_rows(), ctx->gsz, count, out, out_stride, ctx->stream));
-        ctx->launches += 1;
+        // 5th-generation tensor cores, key consumed in its standard layout (tc5_kernels.cu).  Launched in slices of at
+        // most 6 144 bits: every column tile re-reads the digit planes of its launch (12.4 KB per bit), and 6 144 bits
+        // of them (76 MB) stay in L2 next to the streamed key while 18 944 (234 MB) would be re-read from HBM 400 times.
+        const int nslices = (count + 6143) / 6144;
+        const int slice = (((count + nslices - 1) / nslices) + 127) & ~127;
+        for (int b0 = 0; b0 < count; b0 += slice) {
+            const int nb = count - b0 < slice ? count - b0 : slice;
+            CU(launch_tc5_pfks(dl + (size_t)b0 * rows_pad, dh + (size_t)b0 * rows_pad, rows_pad, ctx->pfpksk, kp1, ctx->pf_rows(), ctx->gsz, nb,
+                               out + (size_t)b0 * out_stride, out_stride, ctx->stream));
+            ctx->launches += 1;
+        }
         return TFA_OK;
     }
     CU(launch_gemv_init(out, out_stride, kp1 * ctx->gsz, count, nullptr, 0, nullptr, 0, 0, 0, ctx->stream));
