@@ -121,7 +121,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
     for (int i = tid; i < 256; i += WS_THREADS) sm.tw[i] = a.tw[i];
     if (tid == 0) {
         for (int r = 0; r <= K; r++) {
-            ws_mbar_init(&sm.rfull[r], G);
+            // spectra-ready barriers are shared by pairs of rows (0,1), (2,3), (4): the barrier unit serialises try_waits
+            // at ~95 cycles each, and in steady state the FFT role is far enough ahead for the pair to be complete
+            ws_mbar_init(&sm.rfull[r], G * ((r | 1) <= K ? 2 : 1));
             ws_mbar_init(&sm.rempty[r], WS_MAC_WARPS);
             ws_mbar_init(&sm.bempty[r], WS_MAC_WARPS);
         }
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
                         for (int k2 = 0; k2 < 16; k2++) slot[lane + 16 * k2] = v[rev4(k2)];
                     }
                     __syncwarp();
-                    if (active && lane == 0) ws_mbar_arrive(&sm.rfull[r]);
+                    if (active && lane == 0) ws_mbar_arrive(&sm.rfull[r & ~1]);
                     produced++;
                     WT(WT_F_POST);
                 }
@@ -251,9 +253,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
                 const unsigned parity = level_count & 1;
 #pragma unroll
                 for (int r = 0; r <= K; r++, q++) {
-                    if (r == 0) ws_mbar_wait2(&sm.bfull[0], parity, &sm.rfull[r], parity);
-                    else if (r == BSPLIT) ws_mbar_wait2(&sm.bfull[1], parity, &sm.rfull[r], parity);
-                    else ws_mbar_wait(&sm.rfull[r], parity);
+                    if (r == 0) ws_mbar_wait2(&sm.bfull[0], parity, &sm.rfull[0], parity);
+                    else if (r == BSPLIT && (r & 1) == 0) ws_mbar_wait2(&sm.bfull[1], parity, &sm.rfull[r], parity);
+                    else if (r == BSPLIT) ws_mbar_wait(&sm.bfull[1], parity);
+                    else if ((r & 1) == 0) ws_mbar_wait(&sm.rfull[r], parity);
                     WT(WT_M_WAIT);
                     cd x[G];
 #pragma unroll
