@@ -15,7 +15,7 @@
 // for 60 FMAs per thread), so the two roles use complementary resources; run in separate warps they overlap
 // instead of alternating, with four warps per scheduler instead of two.  The roles have different register
 // needs (FFT: 16 complex + 32 decomposition states; MAC: G*(K+1) complex accumulators), so the register file
-// is re-balanced with setmaxnreg (144 / 112 per thread at G = 3).
+// is re-balanced with setmaxnreg (136 / 120 per thread at G = 3).
 //
 // Bootstrap key: rows [col][p] of (K+1) x 4 KB, stored in consumption order, streamed L2 -> shared memory by
 // the TMA engine (cp.async.bulk, one lane per row) into a ring of K+1 slots (one level); BFULL[0/1] count the
@@ -29,6 +29,9 @@
 
 #define WS_THREADS 512
 #define WS_FFT_THREADS 256
+#ifndef WS_MAC_REGS3
+#define WS_MAC_REGS3 120
+#endif
 #define WS_MAC_WARPS ((WS_THREADS - WS_FFT_THREADS) / 32)
 
 __device__ __forceinline__ unsigned ws_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
     // the phase is long complete, and they serialise): rows [0, BSPLIT) are waited for when the level starts, rows
     // [BSPLIT, K] just before row BSPLIT (the slot of the last row is only refilled at row 0 of the next level).
     constexpr int BSPLIT = (K + 2) / 2;
-    constexpr int MAC_REGS = G >= 3 ? 112 : (G == 2 ? 96 : 72);
+    constexpr int MAC_REGS = G >= 3 ? WS_MAC_REGS3 : (G == 2 ? 96 : 72);
 
     // ---- prologue (all 512 threads) ---------------------------------------------------------------
     for (int i = tid; i < 256; i += WS_THREADS) sm.tw[i] = a.tw[i];
