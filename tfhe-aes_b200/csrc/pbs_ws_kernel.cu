@@ -24,52 +24,7 @@
 // Hand-shake per row r (mbarriers in shared memory): RFULL[r] (one arrival per FFT group (ct, r), MAC threads
 // wait), REMPTY[r] (one arrival per MAC warp, the FFT lanes of row r wait before they overwrite their slot),
 // INV (MAC warps arrive after leaving the Fourier accumulators in the slots, FFT lanes wait).
-#include "cmux_core.cuh"
-#include "kernels.h"
-
-#define WS_THREADS 512
-#define WS_FFT_THREADS 256
-#ifndef WS_MAC_REGS3
-#define WS_MAC_REGS3 120
-#endif
-#define WS_MAC_WARPS ((WS_THREADS - WS_FFT_THREADS) / 32)
-
-__device__ __forceinline__ unsigned ws_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ws_mbar_init(uint64_t *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ws_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void ws_mbar_arrive(uint64_t *bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(ws_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void ws_mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(ws_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void ws_mbar_wait(uint64_t *bar, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra.uni WAIT_DONE;\n\t"
-        "bra.uni WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(ws_smem_u32(bar)), "r"(parity) : "memory");
-}
-// wait for two barriers with one polling loop (the two try_wait latencies overlap)
-__device__ __forceinline__ void ws_mbar_wait2(uint64_t *bar_a, unsigned parity_a, uint64_t *bar_b, unsigned parity_b) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t"
-        "WAIT2_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 q, [%2], %3;\n\t"
-        "and.pred p, p, q;\n\t"
-        "@p bra.uni WAIT2_DONE;\n\t"
-        "bra.uni WAIT2_LOOP;\n\t"
-        "WAIT2_DONE:\n\t}" ::"r"(ws_smem_u32(bar_a)), "r"(parity_a), "r"(ws_smem_u32(bar_b)), "r"(parity_b) : "memory");
-}
-__device__ __forceinline__ void ws_bulk_copy_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ws_smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(ws_smem_u32(bar))
-                 : "memory");
-}
+#include "ws_common.cuh"
 
 template <int K, int G>
 struct WsSmem {
@@ -84,13 +39,6 @@ struct WsSmem {
     uint64_t inv;
     uint64_t pad_;
 };
-
-// modulus switch to 2N: a~ = (a * in_scale [+ pre_add on the body] + 2^53) >> 54
-__device__ __forceinline__ int ws_mod_switch_2n(const PbsArgs &a, int ct, int i) {
-    uint64_t x = a.lwe_in[(size_t)ct * (a.lwe_dim + 1) + i] * a.in_scale;
-    if (i == a.lwe_dim) x += a.pre_add_body;
-    return (int)((x + (1ull << 53)) >> 54) & (2 * POLY_N - 1);
-}
 
 // TIMING (debug launches, PbsArgs::dbg != nullptr): thread 0 (FFT role) and thread 256 (MAC role) of block 0 accumulate
 // clock64() deltas per activity and write them to dbg[0..WT_COUNT).
