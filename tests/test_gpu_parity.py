@@ -317,6 +317,26 @@ def test_opt_integer_stages_bit_exact(engine_opt, oracle_opt):
     assert np.array_equal(got[0], oracle_opt.pfks(4, ct[0]))
 
 
+def test_opt_keyswitches_across_tensor_tiles(engine_opt, oracle_opt):
+    """The tcgen05 keyswitch kernels tile the bits by 128: 300 inputs = two full tiles and a ragged one; extreme words
+    exercise the digit limbs (d = d_lo + 128 d_hi) and the 64-bit recombination.  Bit-exact against the oracle on a
+    sample of rows of every tile and every PFKS key."""
+    rng = np.random.default_rng(21)
+    ct = rng.integers(0, 2 ** 64, (300, oracle_opt.lw), dtype=np.uint64)
+    ct[0, :] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    ct[127, :] = np.uint64(0x8000000000000000)
+    ct[128, :] = np.uint64(0x7FF7FF7FF7FF7FF7)
+    ct[299, ::2] = np.uint64(0)
+    sample = [0, 1, 127, 128, 255, 256, 299]
+    ks = engine_opt.keyswitch(ct)
+    for i in sample:
+        assert np.array_equal(ks[i], oracle_opt.keyswitch(ct[i:i + 1])[0]), f"keyswitch row {i}"
+    for key in range(oracle_opt.k + 1):
+        got = engine_opt.pfks(key, ct)
+        for i in sample:
+            assert np.array_equal(got[i], oracle_opt.pfks(key, ct[i])), f"pfks key {key} row {i}"
+
+
 def test_opt_bootstrap_matches_oracle(engine_opt, oracle_opt):
     o = oracle_opt
     msgs = np.array([0, 1, 1, 0, 1], dtype=np.uint64)
