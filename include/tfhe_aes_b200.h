@@ -112,6 +112,11 @@ int tfa_add_scalar(tfa_ctx *ctx, uint64_t *states, const uint64_t *counters_lo_h
 /* the CTR loop of main.rs:55-64: out[b] = AES(iv + first + b), b < nblk */
 int tfa_aes_ctr(tfa_ctx *ctx, const uint64_t *round_keys, const uint64_t *iv_ct, uint64_t first_lo, uint64_t first_hi,
                 int nblk, uint64_t *out);
+/* The step after the path (transciphering): the reference stops at the encrypted keystream of main.rs:55-64;
+ * XOR with clear data blocks (16 bytes each, AES byte order, e.g. the AES-CTR ciphertext a client uploaded) turns it into
+ * encryptions of the data.  With one message bit per LWE at 2^63 a clear bit adds bit * 2^63 to the body: no bootstrap. */
+int tfa_xor_clear(tfa_ctx *ctx, uint64_t *states, const uint8_t *data, int nblk);
+int tfa_xor_clear_dev(tfa_ctx *ctx, uint64_t *states, const uint8_t *data_dev, int nblk);
 /* one AES round on nblk states (BASELINE config 2): 16*nblk many_sbox + ShiftRows/MixColumns + AddRoundKey */
 int tfa_aes_round(tfa_ctx *ctx, const uint64_t *round_key, uint64_t *states, int nblk);
 /* linear layers alone (server.rs:278-282, mix_columns.rs:4, inv_mix_columns.rs:4, shift_rows.rs:5, inv_shift_rows.rs:5) */

@@ -289,6 +289,29 @@ def test_add_scalar_and_ctr(pkg, engine_test, oracle_test, orc):
         assert o.decrypt_bytes(out[b]) == orc.clear_aes_encrypt(key, (254 + b).to_bytes(16, "big"))
 
 
+def test_ctr_transciphering_xor(pkg, engine_test, oracle_test, orc):
+    """The step after the keystream: Enc(keystream) XOR clear AES-CTR ciphertext = Enc(message), and the
+    CTR entry point with its shared IV bootstrap agrees block by block with add_scalar + aes_encrypt."""
+    o = oracle_test
+    srv = pkg.Server(engine_test)
+    key = bytes.fromhex("000102030405060708090a0b0c0d0e0f")
+    iv = int.from_bytes(bytes.fromhex("f0f1f2f3f4f5f6f7f8f9fafbfcfdfeff"), "big")
+    rk = srv.aes_key_expansion(o.encrypt_bytes(key))
+    iv_ct = o.encrypt_bytes(iv.to_bytes(16, "big"))
+    nblk = 4
+    ks = srv.aes_ctr(rk, iv_ct, nblk, first=0)
+    message = bytes(range(64))
+    stream = b"".join(orc.clear_aes_encrypt(key, ((iv + b) % 2 ** 128).to_bytes(16, "big")) for b in range(nblk))
+    uploaded = bytes(m ^ k for m, k in zip(message, stream))            # what an AES-CTR client sends
+    got = engine_test.xor_clear(ks, uploaded)
+    assert b"".join(o.decrypt_bytes(got[b]) for b in range(nblk)) == message
+    # reference schedule: clone the IV, add_scalar(i), aes_encrypt (main.rs:59-61)
+    st = srv.add_scalar(np.stack([iv_ct] * nblk), list(range(nblk)))
+    enc = engine_test.aes_encrypt(rk, st)
+    for b in range(nblk):
+        assert o.decrypt_bytes(enc[b]) == stream[16 * b:16 * b + 16] == o.decrypt_bytes(ks[b])
+
+
 def test_client_keygen_roundtrip(pkg, orc):
     """Keys generated by the GPU client harness: engine-side encrypt/decrypt round trip, a full S-box,
     and a cross-check of an engine ciphertext with the oracle's decryption under the exported key."""

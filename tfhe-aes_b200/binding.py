@@ -66,6 +66,8 @@ _SIGS = {
     "tfa_add_scalar": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int],
     "tfa_add_scalar_dev": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int],
     "tfa_aes_ctr": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p],
+    "tfa_xor_clear": [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int],
+    "tfa_xor_clear_dev": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int],
     "tfa_aes_ctr_dev": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p],
     "tfa_add_round_key": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int],
     "tfa_mix_columns": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int],
@@ -379,6 +381,13 @@ class Engine:
         out = np.zeros((nblk, 16, 8, self.lw), dtype=np.uint64)
         self._ck(self.lib.tfa_aes_ctr(self.h, _p(rk), _p(iv_ct), first & (2 ** 64 - 1), first >> 64, nblk, _p(out)))
         return out
+
+    def xor_clear(self, states, data: bytes):
+        """Transciphering step: states (keystream ciphertexts) ^= clear data blocks (16 bytes each)."""
+        st = np.array(states, dtype=np.uint64).reshape(-1, 16, 8, self.lw)
+        assert len(data) == 16 * len(st)
+        self._ck(self.lib.tfa_xor_clear(self.h, _p(st), bytes(data), len(st)))
+        return st
 
     def add_round_key(self, states, rk):
         st = np.array(states, dtype=np.uint64).reshape(-1, 16, 8, self.lw)

@@ -547,6 +547,30 @@ extern "C" int tfa_aes_ctr(tfa_ctx *ctx, const uint64_t *round_keys, const uint6
     SYNC();
     return TFA_OK;
 }
+// transciphering step: states ^= clear data (see the header)
+extern "C" int tfa_xor_clear_dev(tfa_ctx *ctx, uint64_t *states, const uint8_t *data_dev, int nblk) {
+    Guard g(ctx);
+    if (nblk < 1 || !states || !data_dev) return ctx->fail(TFA_ERR_PARAM, "xor_clear: bad arguments");
+    if (nblocks_per_byte(ctx) != 8) return ctx->fail(TFA_ERR_UNSUPPORTED, "xor_clear needs 1-bit blocks (client.rs:53-54)");
+    CU(launch_xor_clear(states, data_dev, ctx->lw, (long)nblk * 128, ctx->stream));
+    ctx->launches++;
+    return TFA_OK;
+}
+extern "C" int tfa_xor_clear(tfa_ctx *ctx, uint64_t *states, const uint8_t *data, int nblk) {
+    Guard g(ctx);
+    if (nblk < 1 || !states || !data) return ctx->fail(TFA_ERR_PARAM, "xor_clear: bad arguments");
+    if (nblocks_per_byte(ctx) != 8) return ctx->fail(TFA_ERR_UNSUPPORTED, "xor_clear needs 1-bit blocks (client.rs:53-54)");
+    const size_t sw = (size_t)nblk * 16 * ctx->byte_words();
+    RC(ws_reserve(ctx, sw * 8 + (size_t)nblk * 16 + 512));
+    WSB(d_st, u64, sw); WSB(d_data, uint8_t, (size_t)nblk * 16);
+    H2D(d_st, states, sw);
+    CU(cudaMemcpyAsync(d_data, data, (size_t)nblk * 16, cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_xor_clear(d_st, d_data, ctx->lw, (long)nblk * 128, ctx->stream));
+    ctx->launches++;
+    D2H(states, d_st, sw);
+    SYNC();
+    return TFA_OK;
+}
 // linear layers alone
 extern "C" int tfa_add_round_key(tfa_ctx *ctx, uint64_t *states, const uint64_t *round_key, int nblk) {
     Guard g(ctx);

@@ -63,6 +63,17 @@ cudaError_t launch_add_body(uint64_t *lwe, int words, int count, uint64_t add, c
     add_body_kernel<<<(count + 255) / 256, 256, 0, s>>>(lwe, words, count, add);
     return cudaGetLastError();
 }
+// XOR of encrypted bits with clear bits: bit j of byte `by` of the data adds (bit << 63) to the body of LWE (by, j)
+__global__ void xor_clear_kernel(uint64_t *states, const uint8_t *data, int lw, long nbits) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbits) return;
+    const uint64_t bit = (data[i >> 3] >> (i & 7)) & 1;
+    states[(size_t)i * lw + lw - 1] += bit << 63;
+}
+cudaError_t launch_xor_clear(uint64_t *states, const uint8_t *data, int lw, long nbits, cudaStream_t s) {
+    xor_clear_kernel<<<(unsigned)((nbits + 255) / 256), 256, 0, s>>>(states, data, lw, nbits);
+    return cudaGetLastError();
+}
 __global__ void fill_kernel(uint64_t *dst, long n, uint64_t v) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = v;

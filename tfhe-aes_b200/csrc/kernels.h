@@ -100,6 +100,7 @@ cudaError_t launch_scale_lwe(const uint64_t *in, uint64_t *out, long nwords, uin
 cudaError_t launch_sub_lwe(uint64_t *inout, const uint64_t *sub, long nwords, cudaStream_t s);
 cudaError_t launch_add_body(uint64_t *lwe, int lwe_words, int count, uint64_t add, cudaStream_t s);
 cudaError_t launch_fill_u64(uint64_t *dst, long n, uint64_t v, cudaStream_t s);
+cudaError_t launch_xor_clear(uint64_t *states, const uint8_t *data, int lw, long nbits, cudaStream_t s);
 // trivial GLWE leaves for the CMux tree: out[job][out][leaf][(k+1)N] from lut[job*js + out*os + leaf*N + j]
 cudaError_t launch_tree_leaves(const uint64_t *lut, size_t lut_job_stride, size_t lut_out_stride, int njobs, int nouts,
                                int nleaf, int glwe_dim, uint64_t *out, cudaStream_t s);
