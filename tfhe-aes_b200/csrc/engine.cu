@@ -287,7 +287,7 @@ int dev_pbs(tfa_ctx *ctx, const u64 *in, int count, const u64 *lut, u64 in_scale
     a.lwe_in = in; a.bsk = ctx->bsk_f; a.tw = ctx->tw; a.lut = lut; a.out = out;
     a.in_scale = in_scale; a.pre_add_body = pre_add; a.post_add = post_add; a.lwe_dim = ctx->n; a.count = count;
     // Two schedules of the same arithmetic (measured on B200, PARAM_OPT, 669 steps, one wave of 148 CTAs):
-    //   warp-specialised (pbs_ws_kernel.cu): 10.85 ms at G = 3, 9.9 ms at G = 2, 7.7 ms at G = 1
+    //   warp-specialised (pbs_ws_kernel.cu): 10.6 ms at G = 3, 9.9 ms at G = 2, 7.5 ms at G = 1
     //   phase-synchronous (fp_kernels.cu):   13.1 ms at G = 3
     // The warp-specialised kernel is the default wherever it is instantiated; the phase-synchronous one serves the
     // remaining shapes (K = 1 test parameter sets with G > 1) and stays selectable for comparison.
