@@ -292,8 +292,6 @@ int dev_pbs(tfa_ctx *ctx, const u64 *in, int count, const u64 *lut, u64 in_scale
     // The warp-specialised kernel is the default wherever it is instantiated; the phase-synchronous one serves the
     // remaining shapes (K = 1 test parameter sets with G > 1) and stays selectable for comparison.
     const int G = pick_G(ctx->k, count);
-    static const int stagger = getenv("TFA_PBS_STAGGER") ? atoi(getenv("TFA_PBS_STAGGER")) : 0;
-    a.stagger = stagger;
     static const bool timing = getenv("TFA_PBS_TIMING") != nullptr;
     const bool ws_available = true;   // every (K, G) pick_G returns is instantiated in both kernels
     const bool use_ws = ws_available && ctx->pbs_schedule != 1;

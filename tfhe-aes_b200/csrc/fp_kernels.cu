@@ -166,10 +166,6 @@ __global__ void __launch_bounds__(CMUX_THREADS, 1) pbs_kernel(PbsArgs a) {
     const int my_ct = min(ct0 + min(tid, G - 1), a.count - 1);
     int next_rot = 0;
     if (tid < G) sm.rot[tid] = mod_switch_2n(a, my_ct, 0);
-    if (a.stagger > 0 && (blockIdx.x & 1)) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < a.stagger) {}
-    }
     if (TIMING && tid == 0) { for (int k = 0; k < PT_COUNT; k++) tacc[k] = 0; tlast = clock64(); }
     __syncthreads();
     int q = 0;                                           // next row to consume (uniform over the CTA)

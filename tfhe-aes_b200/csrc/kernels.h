@@ -15,7 +15,6 @@ struct PbsArgs {
     int lwe_dim;
     int count;
     uint64_t *dbg;            // debug: per-phase cycle counters of block 0 (nullptr in production)
-    int stagger;              // cycles by which odd CTAs start late (spreads the L2 demand of the key rows)
 };
 struct VpArgs {
     const double2 *ggsw_f;    // [njobs][nbits][level][row][col][p], bit 0 = LSB
