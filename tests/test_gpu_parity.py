@@ -312,6 +312,19 @@ def test_ctr_transciphering_xor(pkg, engine_test, oracle_test, orc):
         assert o.decrypt_bytes(enc[b]) == stream[16 * b:16 * b + 16] == o.decrypt_bytes(ks[b])
 
 
+@pytest.mark.parametrize("iv,first", [(2 ** 128 - 2, 0), (2 ** 64 - 3, 1), (0x00FF_FFFF_FFFF_FFFF_FFFF_FFFF_FFFF_FF00, 254)])
+def test_ctr_carry_chain_with_shared_iv_bootstrap(pkg, engine_test, oracle_test, orc, iv, first):
+    """tfa_aes_ctr bootstraps the IV bits once and only the carries per block: carries must ripple through every byte,
+    across the 64-bit boundary and wrap at 2^128 exactly as add_scalar (server.rs:172-275) block by block."""
+    o = oracle_test
+    srv = pkg.Server(engine_test)
+    key = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
+    rk = srv.aes_key_expansion(o.encrypt_bytes(key))
+    out = srv.aes_ctr(rk, o.encrypt_bytes(iv.to_bytes(16, "big")), 5, first=first)
+    for b in range(5):
+        assert o.decrypt_bytes(out[b]) == orc.clear_aes_encrypt(key, ((iv + first + b) % 2 ** 128).to_bytes(16, "big")), (hex(iv), first, b)
+
+
 def test_client_keygen_roundtrip(pkg, orc):
     """Keys generated by the GPU client harness: engine-side encrypt/decrypt round trip, a full S-box,
     and a cross-check of an engine ciphertext with the oracle's decryption under the exported key."""
