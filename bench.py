@@ -119,7 +119,8 @@ def run_reference(args):
     if rank != 0:
         return
     vals = []
-    for _ in range(args.warmup_ref):
+    nwarm = max(args.warmup_ref, min(args.warmup, 3))   # a CPU sample is ~2 s: honour --warmup up to 3 samples
+    for _ in range(nwarm):
         cpu_sample(1)
     t_all = time.perf_counter()
     for _ in range(args.steps):
@@ -127,7 +128,7 @@ def run_reference(args):
         vals.append(r)
     per_step = (time.perf_counter() - t_all) / max(1, args.steps)
     v = float(np.mean([r["blocks_per_s"] for r in vals]))
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup_ref,
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": nwarm,
             "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64+f64", "data": "synthetic",
             "config": {"workload": f"aes128_ctr (add_scalar + aes_encrypt = {WOPBS_PER_BLOCK} byte-WoPBS = {PBS_PER_BLOCK_REFERENCE} PBS per block), PARAM_OPT n=669 k=4 N=512; CPU port of the reference path (oracle), bounded sample scaled by the WoPBS count",
                        "note": "the Rust reference (tfhe-rs 0.11.2) cannot be built in this image; README.md:186 quotes 84 s/block/core"},
