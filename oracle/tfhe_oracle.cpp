@@ -66,6 +66,7 @@ struct orc_ctx {
     int n, k, N, M, big;  // big = k*N
     std::vector<cplx> twist;   // [M]  exp(i*pi*j/N)
     std::vector<cplx> wtab;    // [M/2] exp(2*pi*i*j/M)
+    std::vector<double> wstage_fwd, wstage_inv;   // per-stage contiguous copies of wtab (and conjugates), interleaved re/im
     std::vector<int> bitrev;   // [M]
     std::vector<u64> lwe_sk, glwe_sk, bsk, ksk, pfpksk;
     std::vector<double> bsk_f;  // [n][l][k+1][k+1][M][2]
@@ -102,21 +103,30 @@ extern "C" void orc_decompose(uint64_t x, int base_log, int level, int64_t *digi
 // both are exact power-of-two scalings, omitted here.)
 // ------------------------------------------------------------------------------------------------
 static void fft_core(const orc_ctx *c, cplx *a, bool inverse) {
+    // iterative radix-2, decimation in time.  Same operations per element as the textbook loop over std::complex
+    // (product = (ac - bd, ad + bc), then sum / difference); written on the interleaved doubles with per-stage contiguous
+    // twiddles so that the compiler vectorises the butterflies — this is also the CPU arm of bench.py.
     const int M = c->M;
     for (int i = 0; i < M; i++) {
         int j = c->bitrev[i];
         if (i < j) std::swap(a[i], a[j]);
     }
+    double *p = reinterpret_cast<double *>(a);
+    const double *wt = inverse ? c->wstage_inv.data() : c->wstage_fwd.data();
     for (int len = 2; len <= M; len <<= 1) {
-        int half = len >> 1, step = M / len;
-        for (int i = 0; i < M; i += len)
+        const int half = len >> 1;
+        const double *w = wt + 2 * (half - 1);          // stage tables are concatenated: offsets 0, 1, 3, 7, ...
+        for (int i = 0; i < M; i += len) {
+            double *u = p + 2 * i, *v = p + 2 * (i + half);
+#pragma omp simd
             for (int j = 0; j < half; j++) {
-                cplx w = c->wtab[j * step];
-                if (inverse) w = std::conj(w);
-                cplx u = a[i + j], v = a[i + j + half] * w;
-                a[i + j] = u + v;
-                a[i + j + half] = u - v;
+                const double br = v[2 * j], bi = v[2 * j + 1], wr = w[2 * j], wi = w[2 * j + 1];
+                const double tr = br * wr - bi * wi, ti = br * wi + bi * wr;
+                const double ur = u[2 * j], ui = u[2 * j + 1];
+                u[2 * j] = ur + tr; u[2 * j + 1] = ui + ti;
+                v[2 * j] = ur - tr; v[2 * j + 1] = ui - ti;
             }
+        }
     }
 }
 static void fft_forward_signed(const orc_ctx *c, const i64 *re, const i64 *im, cplx *out) {
@@ -160,6 +170,12 @@ extern "C" orc_ctx *orc_create(const orc_params *p) {
     c->twist.resize(c->M); c->wtab.resize(c->M / 2); c->bitrev.resize(c->M);
     for (int j = 0; j < c->M; j++) c->twist[j] = std::polar(1.0, M_PI * j / c->N);
     for (int j = 0; j < c->M / 2; j++) c->wtab[j] = std::polar(1.0, 2.0 * M_PI * j / c->M);
+    for (int len = 2; len <= c->M; len <<= 1)
+        for (int j = 0; j < len / 2; j++) {
+            const cplx w = c->wtab[(size_t)j * (c->M / len)];
+            c->wstage_fwd.push_back(w.real()); c->wstage_fwd.push_back(w.imag());
+            c->wstage_inv.push_back(w.real()); c->wstage_inv.push_back(-w.imag());
+        }
     int lg = 0; while ((1 << lg) < c->M) lg++;
     for (int i = 0; i < c->M; i++) { int r = 0; for (int b = 0; b < lg; b++) if (i >> b & 1) r |= 1 << (lg - 1 - b); c->bitrev[i] = r; }
     return c;
@@ -382,7 +398,14 @@ static void external_product_add(const orc_ctx *c, const double *ggsw_f, int bas
             for (int col = 0; col <= k; col++) {
                 cplx *a = &acc[(size_t)col * M];
                 const cplx *gg = g + (size_t)col * M;
-                for (int j = 0; j < M; j++) a[j] += f[j] * gg[j];
+                const double *fp = reinterpret_cast<const double *>(f.data()), *gp = reinterpret_cast<const double *>(gg);
+                double *ap = reinterpret_cast<double *>(a);
+#pragma omp simd
+                for (int j = 0; j < M; j++) {   // a[j] += f[j] * gg[j], same operation order as std::complex
+                    const double fr = fp[2 * j], fi = fp[2 * j + 1], gr = gp[2 * j], gi = gp[2 * j + 1];
+                    ap[2 * j] += fr * gr - fi * gi;
+                    ap[2 * j + 1] += fr * gi + fi * gr;
+                }
             }
         }
     }
