@@ -121,6 +121,19 @@ HD void fft256_inv_pass1_store(cd (&v)[16], int lane, const cd *tw, cd *xb) {
 #pragma unroll
     for (int n2 = 0; n2 < 16; n2++) xb[xb_idx(n2, lane)] = cmul_conj(v[rev4(n2)], tw[xb_idx(lane, n2)]);
 }
+// batched form (the stores to xb may alias the twiddle table as far as the compiler knows, so it never hoists a twiddle
+// load above the previous store: explicit batches of TWB loads, then TWB products and stores)
+template <int TWB>
+HD void fft256_inv_pass1_store_b(cd (&v)[16], int lane, const cd *tw, cd *xb) {
+#pragma unroll
+    for (int h = 0; h < 16; h += TWB) {
+        cd w[TWB];
+#pragma unroll
+        for (int j = 0; j < TWB; j++) w[j] = tw[xb_idx(lane, h + j)];
+#pragma unroll
+        for (int j = 0; j < TWB; j++) xb[xb_idx(h + j, lane)] = cmul_conj(v[rev4(h + j)], w[j]);
+    }
+}
 // lane = n2.  Out: z[16 n1 + lane] * 256 at v[rev4(n1)] before the final untwist; this applies the
 // untwist conj(phi^n1) and the 1/256 scale and returns natural order in v[n1].
 HD void fft256_inv_pass2(cd (&v)[16], int lane, const cd *xb) {

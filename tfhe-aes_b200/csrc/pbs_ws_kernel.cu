@@ -15,7 +15,7 @@
 // for 60 FMAs per thread), so the two roles use complementary resources; run in separate warps they overlap
 // instead of alternating, with four warps per scheduler instead of two.  The roles have different register
 // needs (FFT: 16 complex + 32 decomposition states; MAC: G*(K+1) complex accumulators), so the register file
-// is re-balanced with setmaxnreg (136 / 120 per thread at G = 3).
+// is re-balanced with setmaxnreg (144 / 112 per thread at G = 3).
 //
 // Bootstrap key: rows [col][p] of (K+1) x 4 KB, stored in consumption order, streamed L2 -> shared memory by
 // the TMA engine (cp.async.bulk, one lane per row) into a ring of K+1 slots (one level); BFULL[0/1] count the
@@ -25,6 +25,33 @@
 // wait), REMPTY[r] (one arrival per MAC warp, the FFT lanes of row r wait before they overwrite their slot),
 // INV (MAC warps arrive after leaving the Fourier accumulators in the slots, FFT lanes wait).
 #include "ws_common.cuh"
+
+// scratch/pbs_lab builds several variants of this file into one binary: each gets its own namespace and launcher name
+#ifndef PBS_WS_NS
+#define PBS_WS_NS ws_default
+#endif
+#ifndef PBS_WS_LAUNCH_NAME
+#define PBS_WS_LAUNCH_NAME launch_pbs_ws
+#endif
+// Tuning switches.  The defaults are the configuration measured best on B200 with scratch/pbs_lab (one wave of 444 ciphertexts,
+// every variant checked bit for bit against the round-1 kernel): 10.41 ms against 10.59 ms.  DESIGN.md §7 lists what was measured
+// for each of them and for the schedules that lost (row-ahead barrier probes, software-pipelined MAC rows, twiddles on the pass-2 side).
+#ifndef WS_MAC_REUSE
+#define WS_MAC_REUSE 1    // FMAs of one key value ordered so that consecutive DFMAs share an operand (a DFMA with three distinct
+#endif                    // register operands issues every 3 cycles on B200, every 2 with one operand reused: scratch/mb_fp64ops.cu)
+#ifndef WS_REVMAP
+#define WS_REVMAP 1       // FFT groups in reverse warp order: the issue arbiter favours high warp ids and the MAC role consumes row 0 first
+#endif
+#ifndef WS_TWB_INV
+#define WS_TWB_INV 8      // inverse pass 1: mid twiddles fetched in batches of 8 (0: one by one, each load behind the previous store)
+#endif
+#ifndef WS_ROT_LATE
+#define WS_ROT_LATE 1     // the next mask element is fetched before the inverse FFT and mod-switched after it
+#endif
+#ifndef WS_DIAG
+#define WS_DIAG 0         // diagnostics of scratch/pbs_lab: each bit removes one piece of work (results are WRONG when != 0)
+#endif
+namespace PBS_WS_NS {
 
 template <int K, int G>
 struct WsSmem {
@@ -39,6 +66,21 @@ struct WsSmem {
     uint64_t inv;
     uint64_t pad_;
 };
+
+// facc[g][c] += x[g] * w for all g, in an order that lets consecutive DFMAs share the key component as one operand: a DFMA with
+// three distinct register operands issues every 3 cycles on B200, with one operand from the reuse cache every 2
+// (scratch/mb_fp64ops.cu).  Per accumulator the order of the two updates is that of cmac (bit-identical results).
+template <int G, int KP1>
+__device__ __forceinline__ void cmac_cols(cd (&facc)[G][KP1], int c, const cd (&x)[G], cd w) {
+#pragma unroll
+    for (int g = 0; g < G; g++) facc[g][c].x = fma(x[g].x, w.x, facc[g][c].x);
+#pragma unroll
+    for (int g = 0; g < G; g++) facc[g][c].y = fma(x[g].x, w.y, facc[g][c].y);
+#pragma unroll
+    for (int g = 0; g < G; g++) facc[g][c].x = fma(-x[g].y, w.y, facc[g][c].x);
+#pragma unroll
+    for (int g = 0; g < G; g++) facc[g][c].y = fma(x[g].y, w.x, facc[g][c].y);
+}
 
 // TIMING (debug launches, PbsArgs::dbg != nullptr): thread 0 (FFT role) and thread 256 (MAC role) of block 0 accumulate
 // clock64() deltas per activity and write them to dbg[0..WT_COUNT).
@@ -102,7 +144,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
         // ================================ FFT warps ================================================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(256 - MAC_REGS));
         const int ftid = WS_FFT_HIGH ? tid - (WS_THREADS - WS_FFT_THREADS) : tid;
+#if WS_REVMAP   // groups in reverse warp order: the issue arbiter favours high warp ids, and the MAC role consumes row 0 first
+        const int gid = 15 - (ftid >> 4), lane = ftid & 15;
+#else
         const int gid = ftid >> 4, lane = ftid & 15;
+#endif
         const bool active = gid < G * (K + 1);
         // group -> polynomial: row-major (r = gid / G, ct = gid % G), so that the two groups of a warp own the same
         // or adjacent rows and the warp-uniform wait below never holds a row-r group back until row r+2 is consumed
@@ -110,7 +156,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
         // Both 16-lane groups of a warp execute ONE instruction stream (a diverged half-warp would pay a full
         // issue slot and a full FP64 pipe pass for 16 lanes): waits are made warp-uniform by waiting for the
         // later row of the two groups; an idle group (gid >= G*(K+1)) runs along with its stores predicated off.
+#if WS_REVMAP
+        const int gid_a = 14 - (ftid >> 5) * 2, gid_b = gid_a + 1;
+#else
         const int gid_a = (ftid >> 5) * 2, gid_b = gid_a + 1;
+#endif
         const int r_a = gid_a / G;
         const int r_b = (gid_b < G * (K + 1)) ? gid_b / G : r_a;
         cd *slot = sm.hs[active ? gid : 0];
@@ -123,42 +173,72 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
 #pragma unroll 1
             for (int i = 0; i < n; i++) {
                 // the mask element of the next step is fetched one step ahead (its latency hides behind a CMux)
+#if !WS_ROT_LATE
                 const int rot_next = (i + 1 < n) ? ws_mod_switch_2n(a, my_ct, i + 1) : 0;
+#endif
                 if (TIMING) { trace_on = blockIdx.x == 0 && (ftid == 0 || ftid == 224) && i >= 100 && i < 104; trace_sec = ftid == 0 ? 0 : 1; }
                 load_decompose_rot<BASE_LOG, LEVELS>(sm.acc[ct][r], lane, rot, v, st_re, st_im);
+#if !WS_ROT_LATE
                 rot = rot_next;
+#endif
                 WT(WT_F_DECOMP);
 #pragma unroll 1
                 for (int lev = LEVELS; lev >= 1; lev--) {
                     if (lev != LEVELS) next_digits<BASE_LOG, LEVELS>(v, st_re, st_im, lev);
                     // first pass in registers; only then wait until the MAC warps have consumed the previous
                     // occupant of the slot (rows of the previous production)
+#if WS_DIAG & 64           // diagnostic (wrong results): no first-pass arithmetic
+                    v[0].x += 1.0;
+#else
                     fft256_fwd_pass1_compute(v, lane, sm.tw);
+#endif
                     WT(WT_F_PASS1);
                     // (every MAC warp releases the rows of a level in order, so the release of row r_b >= r_a implies r_a's)
+#if !(WS_DIAG & 128)
                     if (produced > 0) ws_mbar_wait(&sm.rempty[r_b], (produced - 1) & 1);
+#endif
                     WT(WT_F_WAIT_EMPTY);
                     if (active) fft256_fwd_pass1_store(v, lane, slot);
                     __syncwarp();
+#if WS_DIAG & 8            // diagnostic (wrong results): loads of pass 2 without its arithmetic
+#pragma unroll
+                    for (int n2 = 0; n2 < 16; n2++) v[n2] = slot[xb_idx(lane, n2)];
+#elif WS_DIAG & 16         // diagnostic (wrong results): arithmetic of pass 2 without its loads
+                    fft16<1>(v);
+#else
                     fft256_fwd_pass2(v, lane, slot);
+#endif
                     __syncwarp();
                     if (active) {
 #pragma unroll
                         for (int k2 = 0; k2 < 16; k2++) slot[lane + 16 * k2] = v[rev4(k2)];
                     }
                     __syncwarp();
+#if !(WS_DIAG & 128)
                     if (active && lane == 0) ws_mbar_arrive(&sm.rfull[r & ~1]);
+#endif
                     produced++;
                     WT(WT_F_POST);
                 }
+#if WS_ROT_LATE
+                // raw mask element of the next step: loaded here (registers are free once the digits are consumed), used
+                // after the inverse transform, so that neither its latency nor its registers sit in the decomposition
+                const uint64_t raw_next = a.lwe_in[(size_t)my_ct * (n + 1) + min(i + 1, n - 1)];
+#endif
                 // inverse transform of the Fourier accumulator the MAC warps left in this group's slot
+#if !(WS_DIAG & 128)
                 ws_mbar_wait(&sm.inv, i & 1);
+#endif
                 WT(WT_F_WAIT_INV);
 #pragma unroll
                 for (int k2 = 0; k2 < 16; k2++) v[k2] = slot[lane + 16 * k2];
                 fft256_inv_pass1_compute(v);
                 __syncwarp();
+#if WS_TWB_INV
+                if (active) fft256_inv_pass1_store_b<WS_TWB_INV>(v, lane, sm.tw, slot);
+#else
                 if (active) fft256_inv_pass1_store(v, lane, sm.tw, slot);
+#endif
                 __syncwarp();
                 fft256_inv_pass2(v, lane, slot);
                 if (active) {
@@ -171,6 +251,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
                     }
                 }
                 __syncwarp();
+#if WS_ROT_LATE
+                rot = (int)((raw_next * a.in_scale + (1ull << 53)) >> 54) & (2 * POLY_N - 1);
+#endif
                 WT(WT_F_INV);
             }
             if (TIMING && blockIdx.x == 0 && ftid == 0)
@@ -184,16 +267,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
         auto produce = [&](int q) {               // fetch key row q into slot q % RING (the caller knows it is free)
             const int s = q % RING;
             uint64_t *bar = &sm.bfull[s < BSPLIT ? 0 : 1];
+#if WS_DIAG & 2          // diagnostic (wrong results): 16 bytes per key row instead of 20 KB
+            ws_mbar_arrive_expect_tx(bar, 16);
+            ws_bulk_copy_g2s(&sm.ring[s][0][0], a.bsk + (size_t)q * ROW_ELEMS, 16, bar);
+#else
             ws_mbar_arrive_expect_tx(bar, ROW_BYTES);
             ws_bulk_copy_g2s(&sm.ring[s][0][0], a.bsk + (size_t)q * ROW_ELEMS, ROW_BYTES, bar);
+#endif
         };
         if (p == 0)
             for (int q = 0; q < RING; q++) produce(q);   // nrows >= RING always
         cd facc[G][K + 1];
+        const int n_mac = (WS_DIAG & 128) ? 0 : n;   // diagnostic: no MAC role at all
         unsigned level_count = 0;
         int q = 0;                                // next key row to consume
 #pragma unroll 1
-        for (int i = 0; i < n; i++) {
+        for (int i = 0; i < n_mac; i++) {
             if (TIMING) { trace_on = blockIdx.x == 0 && p == 0 && i >= 100 && i < 104; trace_sec = 2; }
 #pragma unroll
             for (int g = 0; g < G; g++)
@@ -209,14 +298,33 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
                     else if (r == BSPLIT) ws_mbar_wait(&sm.bfull[1], parity);
                     else if ((r & 1) == 0) ws_mbar_wait(&sm.rfull[r], parity);
                     WT(WT_M_WAIT);
+#if WS_DIAG & 32           // diagnostic (wrong results): the MAC role only runs the barrier protocol
+                    if (0) {
+#else
+                    {
+#endif
                     cd x[G];
 #pragma unroll
                     for (int g = 0; g < G; g++) x[g] = sm.hs[r * G + g][p];
 #pragma unroll
                     for (int c = 0; c <= K; c++) {   // key values are streamed one at a time (register budget)
+#if WS_DIAG & 1      // diagnostic (wrong results): one key load per row instead of K+1
+                        const cd w = sm.ring[r][0][p];
+#else
                         const cd w = sm.ring[r][c][p];
+#endif
+#if WS_DIAG & 4      // diagnostic (wrong results): a quarter of the FMAs
+                        if (c == 0) cmac(facc[0][c], x[0], w);
+                        else { facc[0][c].x += w.x; }
+#else
+#if WS_MAC_REUSE
+                        cmac_cols<G, K + 1>(facc, c, x, w);
+#else
 #pragma unroll
                         for (int g = 0; g < G; g++) cmac(facc[g][c], x[g], w);
+#endif
+#endif
+                    }
                     }
                     __syncwarp();
                     if (mlane == 0) {
@@ -268,6 +376,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
     }
 }
 
+}  // namespace PBS_WS_NS
+using namespace PBS_WS_NS;
+
 #define LAUNCH_WS(k, g, bl, lv)                                                                         \
     if (K == k && G == g && base_log == bl && levels == lv) {                                           \
         const size_t smem = sizeof(WsSmem<k, g>);                                                       \
@@ -276,7 +387,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
         pbs_ws_kernel<k, g, bl, lv><<<(a.count + g - 1) / g, WS_THREADS, smem, s>>>(a);                 \
         return cudaGetLastError();                                                                      \
     }
-cudaError_t launch_pbs_ws(int K, int G, int base_log, int levels, const PbsArgs &a, cudaStream_t s) {
+cudaError_t PBS_WS_LAUNCH_NAME(int K, int G, int base_log, int levels, const PbsArgs &a, cudaStream_t s) {
     if (a.dbg && K == 4 && G == 3 && base_log == 8 && levels == 5) {   // per-activity cycle counts (TFA_PBS_TIMING=1)
         const size_t smem = sizeof(WsSmem<4, 3>);
         cudaError_t e = cudaFuncSetAttribute(pbs_ws_kernel<4, 3, 8, 5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -7,7 +7,7 @@
 #define WS_THREADS 512
 #define WS_FFT_THREADS 256
 #ifndef WS_MAC_REGS3
-#define WS_MAC_REGS3 120
+#define WS_MAC_REGS3 112
 #endif
 #define WS_MAC_WARPS ((WS_THREADS - WS_FFT_THREADS) / 32)
 
