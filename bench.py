@@ -139,32 +139,20 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------
-# FIPS-197 AES-128 in the clear, for verifying decrypted outputs (tables from the product's own sbox module)
-def clear_key_expansion(pkg, key):
-    rcon = [0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, 0x1B, 0x36]
-    w = list(key)
-    for i in range(4, 44):
-        t = w[4 * (i - 1):4 * i]
-        if i % 4 == 0:
-            t = [pkg.SBOX[t[1]] ^ rcon[i // 4 - 1], pkg.SBOX[t[2]], pkg.SBOX[t[3]], pkg.SBOX[t[0]]]
-        w += [w[4 * (i - 4) + j] ^ t[j] for j in range(4)]
-    return w
+# Expected values: tests/aes_clear.py = FIPS-197 with a hard-coded S-box, cross-checked against the `cryptography` package
+# when it is importable.  Nothing of the product (its S-box tables, its decryption kernel) takes part in the check:
+# ciphertexts are copied to the host and decrypted here with numpy from the secret key (client.rs:147-175).
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import aes_clear  # noqa: E402
 
 
-def clear_aes_encrypt(pkg, rk, block):
-    s = [b ^ k for b, k in zip(block, rk[:16])]
-    for r in range(1, 11):
-        s = [pkg.SBOX[x] for x in s]
-        s = [s[(i % 4) + 4 * (((i // 4) + (i % 4)) % 4)] for i in range(16)]
-        if r < 10:
-            t = []
-            for c in range(4):
-                a = s[4 * c:4 * c + 4]
-                t += [pkg.mul2(a[0]) ^ pkg.mul3(a[1]) ^ a[2] ^ a[3], a[0] ^ pkg.mul2(a[1]) ^ pkg.mul3(a[2]) ^ a[3],
-                      a[0] ^ a[1] ^ pkg.mul2(a[2]) ^ pkg.mul3(a[3]), pkg.mul3(a[0]) ^ a[1] ^ a[2] ^ pkg.mul2(a[3])]
-            s = t
-        s = [x ^ k for x, k in zip(s, rk[16 * r:16 * r + 16])]
-    return bytes(s)
+def numpy_decrypt_bytes(ct, glwe_sk):
+    """decrypt_without_padding on the host: ct [..][8][lw] uint64, bit j of a byte in LWE j (client.rs:154)"""
+    ct = ct.reshape(-1, ct.shape[-1])
+    with np.errstate(over="ignore"):
+        ph = ct[:, -1] - (ct[:, :-1] * glwe_sk).sum(axis=1, dtype=np.uint64)
+        bits = ((ph + np.uint64(1 << 62)) >> np.uint64(63)).astype(np.uint8) & 1
+    return bytes(np.packbits(bits.reshape(-1, 8), axis=1, bitorder="little").ravel())
 
 
 class DevPtrArray:
@@ -194,6 +182,13 @@ def run_gpu(args):
     torch.cuda.set_stream(stream)
     eng = pkg.Engine(pkg.param_opt(), device=local, stream=stream.cuda_stream)
     lw, B = eng.lw, args.blocks_per_gpu
+    strong = args.total_blocks > 0          # BASELINE config 5: a fixed number of blocks split over the GPUs (main.rs:55-64 with --number-of-outputs)
+    shard_start = 0
+    if strong:
+        shard_start, B = pkg.sharding.shard_range(args.total_blocks, rank, world)
+        if B == 0:
+            raise SystemExit("--total-blocks smaller than the number of GPUs")
+    blocks_per_step = args.total_blocks if strong else B * world
     state_words = 16 * 8 * lw
 
     # ---- keys: generated on rank 0 (client harness), replicated by ONE NCCL broadcast -------------------
@@ -236,16 +231,18 @@ def run_gpu(args):
         dist.broadcast(iv_ct, src=0)
     out = torch.zeros(B * state_words, dtype=torch.int64, device=dev)
 
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-
-    clear_rk = clear_key_expansion(pkg, aes_key)
+    glwe_sk = eng.client_secret_keys()[1]
 
     def expected(counter):
         # FIPS-197 AES-128 in the clear (what client.rs:163-171 gets from the `aes` crate)
-        return clear_aes_encrypt(pkg, clear_rk, ((args.iv + counter) % 2 ** 128).to_bytes(16, "big"))
+        return aes_clear.ctr_block(aes_key, args.iv, counter)
+
+    def decrypt_states(t):
+        """device tensor of states -> bytes, through a host copy and numpy (not the product's decryption kernel)"""
+        return numpy_decrypt_bytes(t.cpu().numpy().view(np.uint64).reshape(-1, lw), glwe_sk)
 
     def step(i):
-        first = pkg.sharding.shard_counters(0, B, i, rank, world)[0]
+        first = i * args.total_blocks + shard_start if strong else pkg.sharding.shard_counters(0, B, i, rank, world)[0]
         eng.aes_ctr_dev(rk.data_ptr(), iv_ct.data_ptr(), first, B, out.data_ptr())
         return first
 
@@ -258,7 +255,7 @@ def run_gpu(args):
     for w in range(args.warmup):
         first = step(w)
     torch.cuda.synchronize()
-    got = eng.client_decrypt_bytes_dev(out.data_ptr(), 16 * B)     # every warm-up block is verified (client.rs:147-175)
+    got = decrypt_states(out)     # every warm-up block is verified (client.rs:147-175)
     for b in range(B):
         assert got[16 * b:16 * b + 16] == expected(first + b), f"rank {rank}: block {first + b} differs from FIPS-197"
     sampler = ClockSampler(local)
@@ -274,9 +271,10 @@ def run_gpu(args):
     sampler.stop_flag = True
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count - launches0
-    got = eng.client_decrypt_bytes_dev(out.data_ptr(), 16 * B)
+    got = decrypt_states(out)
     for b in range(B):
         assert got[16 * b:16 * b + 16] == expected(first + b), f"rank {rank}: block {first + b} differs from FIPS-197"
+    first_device = first
     t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
@@ -284,7 +282,7 @@ def run_gpu(args):
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms, launches = float(tmax[0]), int(tsum[1])
-    blocks_total = B * world * args.steps
+    blocks_total = blocks_per_step * args.steps
     value = blocks_total / (ms * 1e-3)
 
     # ---- end to end through the host C ABI: pinned host buffers, H2D of round keys + IV and D2H of every
@@ -296,10 +294,10 @@ def run_gpu(args):
     iv_h.copy_(iv_ct)
     torch.cuda.synchronize()
     rk_np, iv_np, out_np = rk_h.numpy().view(np.uint64), iv_h.numpy().view(np.uint64), out_h.numpy().view(np.uint64)
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_steps = max(1, args.e2e_steps)
 
     def e2e_step(i):
-        first = (i * world + rank) * B + 100000
+        first = (i * args.total_blocks + shard_start if strong else (i * world + rank) * B) + 100000
         res = eng.lib.tfa_aes_ctr(eng.h, rk_np.ctypes.data, iv_np.ctypes.data, first, 0, B, out_np.ctypes.data)
         assert res == 0, eng.lib.tfa_last_error(eng.h)
         return first
@@ -315,11 +313,70 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t[0])
-    from tfhe_aes_b200 import binding  # noqa: F401
-    dec = eng.client_decrypt_bytes(out_np.reshape(B * 16, 8, lw))
+    dec = numpy_decrypt_bytes(out_np.reshape(-1, lw), glwe_sk)
     for b in range(B):
         assert dec[16 * b:16 * b + 16] == expected(first + b), "e2e output differs from FIPS-197"
-    e2e_value = B * world * e2e_steps / e2e_s
+    e2e_value = blocks_per_step * e2e_steps / e2e_s
+
+    # ---- the other configurations BASELINE.json names, device-resident, CUDA events on the library's stream (rank 0, one GPU) ----
+    configs = None
+    if rank == 0 and not args.no_configs:
+        def timed(fn, reps=1):
+            fn()                                   # warm-up (LUT caches, workspace growth)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps * 1e-3
+        one = torch.zeros(state_words, dtype=torch.int64, device=dev)
+        # config 1: --number-of-outputs 1: add_scalar + aes_encrypt of one block (key expansion is config 3)
+        t_single = timed(lambda: eng.aes_ctr_dev(rk.data_ptr(), iv_ct.data_ptr(), 7, 1, one.data_ptr()), reps=2)
+        assert decrypt_states(one) == expected(7), "config 1 output differs from FIPS-197"
+        # config 2: one AES round = 16 many_sbox (L = 3) + ShiftRows/MixColumns/AddRoundKey, on one block and on a full batch
+        st1 = torch.zeros(state_words, dtype=torch.int64, device=dev)
+        rng = np.random.default_rng(5)
+        clear_states = bytes(rng.integers(0, 256, 16 * B, dtype=np.uint8))
+        clear_rk = bytes(rng.integers(0, 256, 16, dtype=np.uint8))
+        rk1 = torch.zeros(state_words, dtype=torch.int64, device=dev)
+        stB = torch.zeros(B * state_words, dtype=torch.int64, device=dev)
+        eng.client_encrypt_bytes_dev(clear_rk, rk1.data_ptr(), seed=103)
+        eng.client_encrypt_bytes_dev(clear_states, stB.data_ptr(), seed=104)
+        st1.copy_(stB[:state_words])
+        t_round1 = timed(lambda: eng.aes_round_dev(rk1.data_ptr(), st1.data_ptr(), 1), reps=3)
+        stB_in = stB.clone()
+        def round_batch():
+            stB.copy_(stB_in)
+            eng.aes_round_dev(rk1.data_ptr(), stB.data_ptr(), B)
+        t_roundB = timed(round_batch, reps=2)
+        got = decrypt_states(stB)
+        for b in range(B):
+            assert got[16 * b:16 * b + 16] == aes_clear.aes_round(clear_states[16 * b:16 * b + 16], clear_rk), "config 2 output differs from the clear AES round"
+        # config 3: aes_key_expansion (40 SubWord S-boxes + 160 refreshes, 50 dependent stages)
+        key_ct2 = torch.zeros(state_words, dtype=torch.int64, device=dev)
+        rk2 = torch.zeros(11 * state_words, dtype=torch.int64, device=dev)
+        eng.client_encrypt_bytes_dev(aes_key, key_ct2.data_ptr(), seed=105)
+        t_keyexp = timed(lambda: eng.aes_key_expansion_dev(key_ct2.data_ptr(), rk2.data_ptr()))
+        assert decrypt_states(rk2) == b"".join(aes_clear.round_keys(aes_key)), "config 3 round keys differ from FIPS-197"
+        # config 4: aes_decrypt on 16 CTR blocks (the first 16 outputs of the last timed step)
+        n4 = min(16, B)
+        dec4_in = out[:n4 * state_words].clone()
+        dec4 = dec4_in.clone()
+        def decrypt16():
+            dec4.copy_(dec4_in)
+            eng.aes_decrypt_dev(rk.data_ptr(), dec4.data_ptr(), n4)
+        t_dec = timed(decrypt16)
+        got = decrypt_states(dec4)
+        for b in range(n4):
+            assert got[16 * b:16 * b + 16] == ((args.iv + first_device + b) % 2 ** 128).to_bytes(16, "big"), "config 4 output differs from the counter block"
+        configs = {"single_block_latency_s": round(t_single, 4), "aes_round_ms": round(t_round1 * 1e3, 3),
+                   "aes_round_batch_ms": round(t_roundB * 1e3, 3), "aes_round_batch_blocks": B,
+                   "sbox_evals_per_s_measured": 16 * B / t_roundB,
+                   "key_expansion_s": round(t_keyexp, 4), "decrypt_16_blocks_s": round(t_dec, 4), "decrypt_blocks": n4,
+                   "note": "config 1: add_scalar + aes_encrypt of one block (tfa_aes_ctr_dev, nblk = 1); config 2: tfa_aes_round_dev on 1 block and on a batch, "
+                           "sbox_evals_per_s_measured = 16 x batch / time of that batch (many_sbox L = 3 + linear layer); config 3: tfa_aes_key_expansion_dev; "
+                           "config 4: tfa_aes_decrypt_dev on 16 blocks; every output checked against FIPS-197 (tests/aes_clear.py)"}
 
     line = None
     if rank == 0:
@@ -338,7 +395,8 @@ def run_gpu(args):
         k1.record(stream)
         torch.cuda.synchronize()
         pbs_ms = k0.elapsed_time(k1) / reps
-        fp64_peak = eng.measure_fp64_peak()
+        peak_dfma, peak_dmma = eng.measure_fp64_peaks()
+        fp64_peak = max(peak_dfma, peak_dmma)
         achieved = count * PBS_FLOP / (pbs_ms * 1e-3) * 1e-12
         # per-stage share of one step (CUDA events around every launch group)
         eng.profile(True)
@@ -358,11 +416,11 @@ def run_gpu(args):
                    "sbox_evals_per_s": r["evals_per_s"], "note": "CPU restatement of the reference path (oracle), not tfhe-rs; README.md:186 quotes 84 s/block/core"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "u64+f64", "data": "synthetic",
-            "config": {"workload": f"aes128_ctr: {B} CTR blocks per GPU per step (add_scalar + aes_encrypt = {WOPBS_PER_BLOCK} byte-WoPBS; {pbs_per_block(B):.1f} PBS per block with the IV bits bootstrapped once per call, {PBS_PER_BLOCK_REFERENCE} block by block), PARAM_OPT n=669 k=4 N=512",
-                       "blocks_per_gpu": B, "global_blocks_per_step": B * world, "parallelism": f"blocks sharded over {world} GPU(s), keys replicated by NCCL broadcast",
-                       "l2": "inputs larger than L2 (1.04 GB of keys streamed per pass)", "verified": "every output block decrypted and compared with FIPS-197"},
+            "config": {"workload": (f"aes128_ctr: {args.total_blocks} CTR blocks per step split over {world} GPU(s) ({B} on rank 0)" if strong else f"aes128_ctr: {B} CTR blocks per GPU per step") + f" (add_scalar + aes_encrypt = {WOPBS_PER_BLOCK} byte-WoPBS; {pbs_per_block(B):.1f} PBS per block with the IV bits bootstrapped once per call, {PBS_PER_BLOCK_REFERENCE} block by block), PARAM_OPT n=669 k=4 N=512",
+                       "blocks_per_gpu": B, "global_blocks_per_step": blocks_per_step, "parallelism": f"blocks sharded over {world} GPU(s), keys replicated by NCCL broadcast",
+                       "l2": "inputs larger than L2 (1.04 GB of keys streamed per pass and 2 MiB of state per block)", "verified": "every output block decrypted and compared with FIPS-197"},
             "sbox_evals_per_s": value * WOPBS_PER_BLOCK,
             "pbs_per_s": value * pbs_per_block(B),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((11 + 1) * state_words * 8 + 16 * B),
@@ -370,7 +428,8 @@ def run_gpu(args):
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": {"bound": "fp64", "kernel": "pbs_ws_kernel<4,3,8,5>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
-                         "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 figure)", "traffic": NCU_DRAM_BYTES_PER_WAVE * -(-count // 444),
+                         "peak_source": "max of the DFMA and the mma.sync.m8n8k4.f64 microbenchmarks of the FP64 pipe in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                         "peak_dfma": peak_dfma, "peak_dmma": peak_dmma, "traffic": NCU_DRAM_BYTES_PER_WAVE * -(-count // 444),
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one 444-PBS wave (profiles/r1_pbs_ws_kernel_ncu.txt: 346.2 + 4.2 MB) x waves in this launch; algorithmic = 342.5 MB of key per wave",
                          "launch_ms": pbs_ms, "pbs_per_launch": count, "flop_per_pbs": PBS_FLOP,
                          "bsk_hbm_gbs": BSK_BYTES * -(-count // (3 * 148)) / (pbs_ms * 1e-3) * 1e-9, "hbm_peak_gbs": hbm,
@@ -380,6 +439,9 @@ def run_gpu(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if configs:
+            line["baseline_configs"] = configs
+            line["sbox_evals_per_s_measured"] = configs["sbox_evals_per_s_measured"]
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -393,11 +455,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--blocks-per-gpu", type=int, default=148)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--iv", type=int, default=0)
     ap.add_argument("--key", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config 1-4 measurements (rank 0)")
+    ap.add_argument("--total-blocks", type=int, default=0, help="strong scaling (BASELINE config 5): this many blocks per step split over the GPUs")
     ap.add_argument("--warmup-ref", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -66,6 +66,9 @@ int tfa_ctx_load_keys(tfa_ctx *ctx, const uint64_t *bsk, const uint64_t *ksk, co
  * from the rank that called tfa_ctx_load_keys / tfa_client_keygen.  tfa_ctx_alloc_keys allocates them
  * on a receiving rank; tfa_ctx_keys_ready marks them valid after the broadcast. */
 int tfa_ctx_alloc_keys(tfa_ctx *ctx);
+/* at most 8 buffers; at PARAM_OPT three: Fourier BSK (342.5 MB), PFPKSK (629.5 MB) and KSK (65.9 MB) in the standard u64 layouts
+ * the tcgen05 kernels consume = 1.04 GB.  The mma.sync fallback layouts follow only when the context uses those kernels
+ * (a shape the tcgen05 kernels do not take, or TFA_KS_IMMA / TFA_PFKS_IMMA set in the environment at tfa_ctx_create). */
 int tfa_ctx_key_buffers(tfa_ctx *ctx, void **dev_ptrs /* [8] */, size_t *bytes /* [8] */, int *count);
 int tfa_ctx_keys_ready(tfa_ctx *ctx);
 int tfa_ctx_synchronize(tfa_ctx *ctx);
@@ -77,7 +80,8 @@ int tfa_ctx_profile_report(tfa_ctx *ctx, double *ms_per_stage /* [10] */, int *l
  * 2 = warp-specialised kernel.  For tests and measurements; unsupported shapes fall back to the automatic choice. */
 int tfa_ctx_set_pbs_schedule(tfa_ctx *ctx, int schedule);
 /* DFMA microbenchmark: measured FP64 pipe peak of the device in TFLOP/s (roofline denominator) */
-int tfa_measure_fp64_peak(tfa_ctx *ctx, double *tflops);
+int tfa_measure_fp64_peak(tfa_ctx *ctx, double *tflops);   /* max of the two below */
+int tfa_measure_fp64_peaks(tfa_ctx *ctx, double *dfma_tflops, double *dmma_tflops); /* FP64 pipe: DFMA and mma.sync.m8n8k4.f64 microbenchmarks */
 /* number of kernels this library launched on the context since creation (bench.py's gpu_launches) */
 uint64_t tfa_ctx_launch_count(const tfa_ctx *ctx);
 
@@ -154,8 +158,14 @@ int tfa_vertical_packing(tfa_ctx *ctx, const uint64_t *lut, int nouts, int npoly
 int tfa_fourier_forward(tfa_ctx *ctx, const uint64_t *polys, int count, double *out);
 
 /* ---- client side (client.rs:70-175): key generation, encryption, decryption on the GPU.
- * Trusted-side harness so that benchmarks and examples are self-contained; not part of the server path. */
+ * Trusted-side harness so that benchmarks and examples are self-contained; not part of the server path.
+ * Randomness is the ChaCha20 key stream under a 256-bit key.  seed = 0: the key comes from the operating system
+ * (getrandom), fresh for every call, as tfhe-rs seeds its generator.  seed != 0: the key is a function of the seed only
+ * -- reproducible material for tests and benchmarks, INSECURE: whoever knows the seed regenerates the secret keys, and two
+ * encryption calls with the same non-zero seed reuse masks and noise.  Production users load tfhe-rs keys with
+ * tfa_ctx_load_keys instead. */
 int tfa_client_keygen(tfa_ctx *ctx, uint64_t seed); /* generates secret keys + BSK/KSK/PFPKSK and loads them */
+void tfa_rng_block(const uint32_t key[8], uint64_t nonce, uint64_t counter, uint64_t out[8]); /* ChaCha20 block (64-bit counter / nonce), host; for tests */
 int tfa_client_encrypt_bytes(tfa_ctx *ctx, const uint8_t *bytes, int count, uint64_t seed, uint64_t *out /* [count][8][lw] */);
 int tfa_client_decrypt_bytes(tfa_ctx *ctx, const uint64_t *ct, int count, uint8_t *bytes_out);
 int tfa_client_encrypt_bytes_dev(tfa_ctx *ctx, const uint8_t *bytes_host, int count, uint64_t seed, uint64_t *out_dev);

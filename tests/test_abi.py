@@ -76,3 +76,18 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) and "emu" not in f:
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "tfhe_oracle" not in txt and "import orc" not in txt, f
+
+
+def test_client_generator_is_chacha20(pkg):
+    """The client harness draws masks, key bits and noise from the ChaCha20 key stream (csrc/client.cu): RFC 7539 §2.3.2
+    block-function vector (key 00..1f, counter word 1, nonce 00:00:00:09 00:00:00:4a 00:00:00:00)."""
+    lib = pkg.load_library()
+    key = (C.c_uint32 * 8)(*[int.from_bytes(bytes(range(4 * i, 4 * i + 4)), "little") for i in range(8)])
+    out = (C.c_uint64 * 8)()
+    lib.tfa_rng_block.argtypes = [C.POINTER(C.c_uint32), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.tfa_rng_block.restype = None
+    # RFC words 12..15 = 00000001 09000000 4a000000 00000000 -> 64-bit counter = words 12,13 and 64-bit nonce = words 14,15
+    lib.tfa_rng_block(key, 0x000000004a000000, (0x09000000 << 32) | 1, out)
+    stream = b"".join(int(v).to_bytes(8, "little") for v in out)
+    assert stream.hex() == ("10f1e7e4d13b5915500fdd1fa32071c4c7d1f4c733c068030422aa9ac3d46c4e"
+                            "d2826446079faa0914c2d705d98b02a2b5129cd1de164eb9cbd083e8a2503c4e")

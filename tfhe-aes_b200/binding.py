@@ -93,6 +93,7 @@ _SIGS = {
     "tfa_ctx_set_pbs_schedule": [C.c_void_p, C.c_int],
     "tfa_ctx_profile_report": [C.c_void_p, C.c_void_p, C.c_void_p],
     "tfa_measure_fp64_peak": [C.c_void_p, C.POINTER(C.c_double)],
+    "tfa_measure_fp64_peaks": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "tfa_lut_size": [C.c_void_p, C.c_int],
 }
 
@@ -243,6 +244,12 @@ class Engine:
         cnt = np.zeros(10, dtype=np.int32)
         self._ck(self.lib.tfa_ctx_profile_report(self.h, _p(ms), _p(cnt)))
         return {n: (float(ms[i]), int(cnt[i])) for i, n in enumerate(self.STAGES) if cnt[i]}
+
+    def measure_fp64_peaks(self):
+        """(DFMA, DMMA) microbenchmarks of the FP64 pipe, TFLOP/s"""
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.lib.tfa_measure_fp64_peaks(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def measure_fp64_peak(self):
         v = C.c_double()

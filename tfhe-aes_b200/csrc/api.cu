@@ -3,6 +3,7 @@
 // loops of the reference (server.rs:47-50, 59-61, 76-78, 88-91, 100-102) become one batched pass
 // over all bytes of all resident blocks.
 #include <cstring>
+#include <mutex>
 #include "engine.h"
 
 static int ilog2u(uint64_t v) { int r = 0; while (v > 1) { v >>= 1; r++; } return r; }
@@ -11,11 +12,10 @@ static int ilog2u(uint64_t v) { int r = 0; while (v > 1) { v >>= 1; r++; } retur
 // tables (table.rs:2-37 = FIPS-197 S-box, generated from the field arithmetic) and sbox.rs:20-42
 // ------------------------------------------------------------------------------------------------
 static uint8_t SBOX[256], INV_SBOX[256];
-static bool tables_ready = false;
+static std::once_flag tables_once;   // process-wide tables, contexts on several threads may race to build them
 static uint8_t xtime(uint8_t x) { return (uint8_t)((x << 1) ^ ((x & 0x80) ? 0x1B : 0)); }
 static uint8_t gf_mul(uint8_t a, uint8_t b) { uint8_t r = 0; while (b) { if (b & 1) r ^= a; a = xtime(a); b >>= 1; } return r; }
-static void init_tables() {
-    if (tables_ready) return;
+static void build_tables() {
     for (int x = 0; x < 256; x++) {
         uint8_t inv = 0;
         if (x) for (int y = 1; y < 256; y++) if (gf_mul((uint8_t)x, (uint8_t)y) == 1) { inv = (uint8_t)y; break; }
@@ -24,8 +24,8 @@ static void init_tables() {
         s ^= 0x63;
         SBOX[x] = s; INV_SBOX[s] = (uint8_t)x;
     }
-    tables_ready = true;
 }
+static void init_tables() { std::call_once(tables_once, build_tables); }
 
 // ------------------------------------------------------------------------------------------------
 // gen_lut (gen_lut.rs:9-42)

@@ -1,33 +1,79 @@
 // client.cu — trusted-side harness on the GPU: key generation, encryption and decryption
 // (what client.rs:70-175 does through tfhe-rs gen_keys_radix / WopbsKey::new_wopbs_key_only_for_wopbs /
 // encrypt_without_padding / decrypt_without_padding).  It exists so that benchmarks, examples and the
-// multi-GPU path are self-contained; it is NOT on the server hot path.  The generator is a counter-based
-// hash (SplitMix64 finaliser), adequate for tests and benchmarks, not a CSPRNG.
+// multi-GPU path are self-contained; it is NOT on the server hot path.
+//
+// Randomness: every mask word, secret-key bit and noise sample is a word of the ChaCha20 key stream (the 64-bit
+// counter / 64-bit nonce variant) under a 256-bit key: word idx of stream s = word idx mod 8 of block idx / 8 with
+// nonce s, so any word is computed independently by the thread that needs it (counter-based, no state).  With
+// seed = 0 the key comes from the operating system (getrandom) and is fresh for every key generation and for every
+// encryption call, as tfhe-rs seeds its CSPRNG (client.rs:106, :128).  A non-zero seed derives the key from the seed
+// alone: reproducible material for tests and benchmarks, INSECURE (anyone who knows the seed regenerates the keys).
 #include <cmath>
 #include <cstring>
+#include <sys/random.h>
 #include "engine.h"
 
 int prepare_keys_from_device(tfa_ctx *ctx, const u64 *bsk_std_dev);  // engine.cu
 int alloc_key_staging(tfa_ctx *ctx);                                   // engine.cu
 
-__host__ __device__ static inline u64 mix64(u64 z) {
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
+struct RngKey { uint32_t k[8]; };
+__host__ __device__ static inline uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+#define CHACHA_QR(a, b, c, d) a += b; d = rotl32(d ^ a, 16); c += d; b = rotl32(b ^ c, 12); a += b; d = rotl32(d ^ a, 8); c += d; b = rotl32(b ^ c, 7)
+// words 2w, 2w+1 of ChaCha20 block `counter` under (key, nonce) as one u64
+__host__ __device__ static inline u64 chacha20_word(const RngKey &key, u64 nonce, u64 counter, int w) {
+    uint32_t x[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key.k[0], key.k[1], key.k[2], key.k[3], key.k[4], key.k[5], key.k[6], key.k[7],
+                      (uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)nonce, (uint32_t)(nonce >> 32)};
+    uint32_t s[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = x[i];
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        CHACHA_QR(x[0], x[4], x[8], x[12]); CHACHA_QR(x[1], x[5], x[9], x[13]); CHACHA_QR(x[2], x[6], x[10], x[14]); CHACHA_QR(x[3], x[7], x[11], x[15]);
+        CHACHA_QR(x[0], x[5], x[10], x[15]); CHACHA_QR(x[1], x[6], x[11], x[12]); CHACHA_QR(x[2], x[7], x[8], x[13]); CHACHA_QR(x[3], x[4], x[9], x[14]);
+    }
+    u64 lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)      // static indexing only (keeps x[] in registers); w is in 0..7
+        if (i == w) { lo = x[2 * i] + s[2 * i]; hi = x[2 * i + 1] + s[2 * i + 1]; }
+    return lo | (hi << 32);
 }
-__host__ __device__ static inline u64 rnd(u64 seed, u64 stream, u64 idx) {
-    return mix64(mix64(seed + 0x9E3779B97F4A7C15ull * (stream + 1)) ^ (idx * 0xD6E8FEB86659FD93ull + 0x2545F4914F6CDD1Dull));
-}
-__device__ static inline u64 gauss_noise(u64 seed, u64 stream, u64 idx, double std_scaled) {
-    const double u1 = ((double)(rnd(seed, stream, 2 * idx) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-    const double u2 = ((double)(rnd(seed, stream, 2 * idx + 1) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+__host__ __device__ static inline u64 rnd(const RngKey &key, u64 stream, u64 idx) { return chacha20_word(key, stream, idx >> 3, (int)(idx & 7)); }
+__device__ static inline u64 gauss_noise(const RngKey &key, u64 stream, u64 idx, double std_scaled) {
+    const double u1 = ((double)(rnd(key, stream, 2 * idx) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    const double u2 = ((double)(rnd(key, stream, 2 * idx + 1) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
     const double g = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
     return (u64)__double2ll_rn(g * std_scaled);
+}
+// seed = 0: 256 bits from the operating system; otherwise a key that is a function of the seed only (tests, benchmarks)
+static int make_rng_key(tfa_ctx *ctx, uint64_t seed, RngKey *key) {
+    if (seed == 0) {
+        size_t got = 0;
+        while (got < sizeof(key->k)) {
+            ssize_t r = getrandom((char *)key->k + got, sizeof(key->k) - got, 0);
+            if (r < 0) return ctx->fail(TFA_ERR_STATE, "getrandom failed: no entropy for key generation / encryption");
+            got += (size_t)r;
+        }
+        return TFA_OK;
+    }
+    const RngKey base = {{0x74666131u, 0x2d746573u, 0x742d6b65u, 0x79000000u, (uint32_t)seed, (uint32_t)(seed >> 32), 0x5eed5eedu, 0x0badc0deu}};
+    for (int i = 0; i < 4; i++) {
+        const u64 w = chacha20_word(base, 0x7365656473ull, 0, i);
+        key->k[2 * i] = (uint32_t)w; key->k[2 * i + 1] = (uint32_t)(w >> 32);
+    }
+    return TFA_OK;
+}
+
+// the generator's block function on the host, so that the CPU test-suite can pin it to the RFC 7539 §2.3.2 vector
+extern "C" void tfa_rng_block(const uint32_t key[8], uint64_t nonce, uint64_t counter, uint64_t out[8]) {
+    RngKey k;
+    memcpy(k.k, key, sizeof(k.k));
+    for (int w = 0; w < 8; w++) out[w] = chacha20_word(k, nonce, counter, w);
 }
 
 // ---- LWE encryption: one CTA per ciphertext --------------------------------------------------------
 // out[row*out_stride + t] mask, body at column dim.  plaintext per row from `pt` (or computed for the KSK).
-__global__ void lwe_encrypt_kernel(const u64 *__restrict__ sk, int dim, u64 seed, u64 stream, double std_scaled, const u64 *__restrict__ pt,
+__global__ void lwe_encrypt_kernel(const u64 *__restrict__ sk, int dim, RngKey seed, u64 stream, double std_scaled, const u64 *__restrict__ pt,
                                    int ksk_levels, int ksk_base_log, const u64 *__restrict__ ksk_in_key, u64 *__restrict__ out, int out_stride) {
     __shared__ u64 red[256];
     const long row = blockIdx.x;
@@ -59,7 +105,7 @@ __global__ void lwe_encrypt_kernel(const u64 *__restrict__ sk, int dim, u64 seed
 // mode 1 (PFPKSK): q = ((key*(big+1) + j)*L + lev); scal = (-z_j)<<sh (z_big = -1); key<k: scal*S_key; key==k: -scal
 template <int K>
 __global__ void __launch_bounds__(512) glwe_keygen_kernel(int mode, const u64 *__restrict__ lwe_sk, const u64 *__restrict__ glwe_sk, int levels,
-                                                         int base_log, int big, u64 seed, u64 stream, double std_scaled, u64 *__restrict__ out) {
+                                                         int base_log, int big, RngKey seed, u64 stream, double std_scaled, u64 *__restrict__ out) {
     __shared__ u64 A[K][512];
     __shared__ uint8_t S[K][512];
     const long q = blockIdx.x;
@@ -119,12 +165,14 @@ __global__ void lwe_decrypt_bits_kernel(const u64 *__restrict__ sk, int dim, con
     if (threadIdx.x == 0) bits[row] = (uint8_t)(((c[dim] - red[0] + (1ull << 62)) >> 63) & 1);
 }
 
-extern "C" int tfa_client_keygen(tfa_ctx *ctx, uint64_t seed) {
+extern "C" int tfa_client_keygen(tfa_ctx *ctx, uint64_t seed_u64) {
     RC(tfa_ctx_alloc_keys(ctx));
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     RC(alloc_key_staging(ctx));
     const int n = ctx->n, k = ctx->k, big = ctx->big;
+    RngKey seed;
+    RC(make_rng_key(ctx, seed_u64, &seed));
     ctx->h_lwe_sk.resize(n); ctx->h_glwe_sk.resize(big);
     for (int i = 0; i < n; i++) ctx->h_lwe_sk[i] = rnd(seed, 1, i) & 1;
     for (int i = 0; i < big; i++) ctx->h_glwe_sk[i] = rnd(seed, 2, i) & 1;
@@ -161,8 +209,10 @@ extern "C" int tfa_client_keygen(tfa_ctx *ctx, uint64_t seed) {
     return rc;
 }
 
-static int encrypt_bytes_dev_nolock(tfa_ctx *ctx, const uint8_t *bytes, int count, uint64_t seed, u64 *out_dev) {
+static int encrypt_bytes_dev_nolock(tfa_ctx *ctx, const uint8_t *bytes, int count, uint64_t seed_u64, u64 *out_dev) {
     if (!ctx->d_glwe_sk) return ctx->fail(TFA_ERR_STATE, "client keys not generated (tfa_client_keygen)");
+    RngKey seed;
+    RC(make_rng_key(ctx, seed_u64, &seed));
     std::vector<u64> pt((size_t)count * 8);
     for (int i = 0; i < count; i++) for (int j = 0; j < 8; j++) pt[(size_t)i * 8 + j] = (u64)((bytes[i] >> j) & 1) << 63;  // client.rs:126-138
     u64 *d_pt = nullptr;

@@ -21,10 +21,13 @@ struct tfa_ctx {
 
     // prepared keys (device)
     double2 *bsk_f;        // [n][pbs_level][k+1][k+1][256]
-    uint8_t *kp_ksk;       // keyswitch key, int8-limb tensor layout [ntiles][kchunks][2048]   (imma_kernels.cu)
-    uint8_t *kp_pfpksk;    // PFPKSK list, same layout [k+1][ntiles][kchunks][2048]
-    u64 *ksk;              // standard-domain staging, only alive during key preparation: [big*ks_level][ks_cols_pad]
-    u64 *pfpksk;           //   [k+1][(big+1)*pfks_level][gsz]
+    u64 *ksk;              // keyswitch key, standard domain [big*ks_level][ks_cols_pad]: the B operand of the tcgen05 keyswitch as it lies
+    u64 *pfpksk;           // PFPKSK list, standard domain [k+1][(big+1)*pfks_level][gsz]: the B operand of the tcgen05 PFKS
+    // mma.sync fallback layouts: allocated, prepared and broadcast only when the fallback kernels will run (a shape the tcgen05
+    // kernels do not take, or TFA_KS_IMMA / TFA_PFKS_IMMA set): +0.70 GB at PARAM_OPT otherwise
+    uint8_t *kp_ksk;       // int8-limb fragment layout [ntiles][kchunks][2048]   (imma_kernels.cu)
+    uint8_t *kp_pfpksk;    // same, [k+1][ntiles][kchunks][2048]
+    bool imma_ks, imma_pfks;
     double2 *tw;           // 256 mid twiddles (twiddle_host.h)
     int ks_cols_pad;
     bool keys_allocated, keys_ready;
@@ -45,6 +48,12 @@ struct tfa_ctx {
     // bump workspace
     char *ws;
     size_t ws_cap, ws_off;
+    // pinned staging ring for the small host-built tables of the linear layers (gather lists): the copy to the device is
+    // asynchronous, and a half of the ring is only reused after the stream has passed the event recorded when it was last left
+    char *pin;
+    size_t pin_cap, pin_off;
+    cudaEvent_t pin_ev[2];
+    bool pin_ev_valid[2];
 
     size_t bsk_f_bytes() const { return (size_t)n * p.pbs_level * (k + 1) * 256 * (k + 1) * sizeof(double2); }
     size_t ksk_bytes() const { return (size_t)big * p.ks_level * ks_cols_pad * 8; }

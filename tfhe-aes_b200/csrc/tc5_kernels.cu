@@ -240,12 +240,9 @@ bool tc5_ks_supported(int ncols, int key_pitch_cols, int rows_pad) { return ncol
 template <int DL>
 static cudaError_t t5_launch(const CUtensorMap &map_dl, const CUtensorMap &map_dh, const CUtensorMap &map_key, const Tc5Args &a, dim3 grid, cudaStream_t s) {
     const size_t smem = (size_t)T5_STAGES(DL) * T5_STAGE_BYTES(DL) + 1024 + 128;   // + alignment slack + barriers
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc5_keyswitch_kernel<DL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    // per launch, as the PBS and vertical-packing launchers do: the attribute is per device and a process may hold contexts on several
+    cudaError_t e = cudaFuncSetAttribute(tc5_keyswitch_kernel<DL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     tc5_keyswitch_kernel<DL><<<grid, T5_THREADS, smem, s>>>(map_dl, map_dh, map_key, a);
     return cudaGetLastError();
 }

@@ -119,7 +119,8 @@ private:
 
 class Client {  // client.rs:59-175 (trusted side: keygen, encrypt, decrypt + verify) on the GPU harness
 public:
-    Client(Engine &engine, size_t number_of_outputs, u128 iv, u128 key, u64 seed = 1) : e(engine), n_out(number_of_outputs), iv_(iv), key_(key) {
+    // seed 0 = keys and encryption randomness from the operating system's entropy; a non-zero seed is reproducible and INSECURE (tests)
+    Client(Engine &engine, size_t number_of_outputs, u128 iv, u128 key, u64 seed = 0) : e(engine), n_out(number_of_outputs), iv_(iv), key_(key), seed_(seed) {
         e.check(tfa_client_keygen(e.ctx, seed));    // gen_keys_radix + new_wopbs_key_only_for_wopbs (client.rs:106-107)
     }
     static void to_bytes(u128 v, uint8_t out[16]) { for (int i = 0; i < 16; i++) out[i] = (uint8_t)(v >> (8 * (15 - i))); }  // MSB byte first (client.rs:126-129)
@@ -128,8 +129,8 @@ public:
         uint8_t kb[16], ib[16];
         to_bytes(key_, kb); to_bytes(iv_, ib);
         State k(e.state_words()), i(e.state_words());
-        e.check(tfa_client_encrypt_bytes(e.ctx, kb, 16, 11, k.data()));
-        e.check(tfa_client_encrypt_bytes(e.ctx, ib, 16, 12, i.data()));
+        e.check(tfa_client_encrypt_bytes(e.ctx, kb, 16, seed_ ? seed_ + 11 : 0, k.data()));
+        e.check(tfa_client_encrypt_bytes(e.ctx, ib, 16, seed_ ? seed_ + 12 : 0, i.data()));
         return {i, k};
     }
     std::vector<uint8_t> decrypt(const std::vector<u64> &states) const {
@@ -145,6 +146,7 @@ private:
     Engine &e;
     size_t n_out;
     u128 iv_, key_;
+    u64 seed_;
 };
 
 // FIPS-197 AES-128 in the clear (the `aes` crate of client.rs:163-171), for client_decrypt_and_verify
