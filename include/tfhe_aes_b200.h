@@ -103,6 +103,12 @@ int tfa_many_sbox(tfa_ctx *ctx, const uint64_t *bytes_in, int nct, int inv, uint
 /* aes_key_expansion (server.rs:107-167).  rcon_ct: [10][8][lw] encryptions of RCON (server.rs:139-140)
  * or NULL for trivial (noise-free) encryptions, which decrypt identically. */
 int tfa_aes_key_expansion(tfa_ctx *ctx, const uint64_t *key_ct, const uint64_t *rcon_ct, uint64_t *round_keys_out);
+/* AES-192 / AES-256 on the same stages (the reference is AES-128 only): key_ct [key_bytes][8][lw] with key_bytes =
+ * 16, 24 or 32, rk_out [key_bytes/4 + 7][16][8][lw]; rounds = 10, 12 or 14.  Every round-key byte is refreshed to noise level 1 as
+ * server.rs:149-150 does for AES-128. */
+int tfa_aes_key_expansion_ex(tfa_ctx *ctx, const uint64_t *key_ct, int key_bytes, const uint64_t *rcon_ct_or_null, uint64_t *rk_out);
+int tfa_aes_encrypt_ex(tfa_ctx *ctx, const uint64_t *round_keys, uint64_t *states_inout, int nblk, int rounds);
+int tfa_aes_decrypt_ex(tfa_ctx *ctx, const uint64_t *round_keys, uint64_t *states_inout, int nblk, int rounds);
 /* aes_encrypt (server.rs:39-64) / aes_decrypt (server.rs:67-105), batched over nblk states in place */
 int tfa_aes_encrypt(tfa_ctx *ctx, const uint64_t *round_keys, uint64_t *states, int nblk);
 int tfa_aes_decrypt(tfa_ctx *ctx, const uint64_t *round_keys, uint64_t *states, int nblk);

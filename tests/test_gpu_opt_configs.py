@@ -225,3 +225,54 @@ def test_opt_client_generated_noise(pkg):
     assert len(err) >= 4000
     assert abs(err.std() / (p.pfks_std * two64) - 1) < 0.1, err.std()
     e.close()
+
+
+# ---- boundary: the reference's call pattern (one block per rayon worker on a shared &Server, main.rs:55-64) ----------------
+def test_opt_concurrent_per_block_calls_are_coalesced(pkg, engine_opt, oracle_opt):
+    """16 threads each run add_scalar + aes_encrypt on ONE block through the host C ABI, concurrently, as the reference's rayon
+    loop does.  The library merges concurrent calls into one batch: every thread gets its own block's result (FIPS-197), and the
+    16 per-block calls together take as long as one 16-block call (within 10 %; measured 0.99 on a B200) instead of 16 times longer."""
+    import threading
+    import time
+    o = oracle_opt
+    srv = pkg.Server(engine_opt)
+    rk = srv.aes_key_expansion(o.encrypt_bytes(KEY))
+    iv = 2 ** 64 - 9
+    iv_ct = o.encrypt_bytes(iv.to_bytes(16, "big"))
+    nthreads = 16
+
+    def batched():
+        st = np.stack([iv_ct] * nthreads)
+        st = srv.add_scalar(st, list(range(nthreads)))
+        return srv.aes_encrypt(rk, st)
+    batched()                                   # warm-up: workspace growth, LUT caches
+    t0 = time.perf_counter()
+    ref = batched()
+    t_batch = time.perf_counter() - t0
+    out = [None] * nthreads
+
+    def worker(i):
+        st = srv.add_scalar(iv_ct[None].copy(), [i])
+        out[i] = srv.aes_encrypt(rk, st)[0]
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(nthreads)]
+    t0 = time.perf_counter()
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    t_threads = time.perf_counter() - t0
+    for i in range(nthreads):
+        want = aes_clear.ctr_block(KEY, iv, i)
+        assert o.decrypt_bytes(out[i]) == want and o.decrypt_bytes(ref[i]) == want, i
+    print(f"16 concurrent per-block calls: {t_threads:.3f} s, one 16-block call: {t_batch:.3f} s, ratio {t_threads / t_batch:.2f}")
+    assert t_threads < 1.10 * t_batch, (t_threads, t_batch)
+
+
+def test_opt_aes256_block(pkg, engine_opt, oracle_opt):
+    """FIPS-197 Appendix C.3 at PARAM_OPT: AES-256 key expansion (15 round keys, 52 SubWord bytes) + 14 rounds."""
+    o = oracle_opt
+    key, pt = bytes(range(32)), bytes.fromhex("00112233445566778899aabbccddeeff")
+    rk = engine_opt.aes_key_expansion_ex(o.encrypt_bytes(key))
+    assert b"".join(o.decrypt_bytes(r) for r in rk) == b"".join(aes_clear.round_keys(key))
+    enc = engine_opt.aes_crypt_ex(rk, o.encrypt_bytes(pt)[None])
+    assert o.decrypt_bytes(enc[0]).hex() == "8ea2b7ca516745bfeafc49904b496089"

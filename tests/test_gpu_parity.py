@@ -501,3 +501,21 @@ def test_cli_mirrors_reference_driver(pkg):
     r = subprocess.run([cli, "--number-of-outputs", "3", "--iv", "254", "--key", "12345678901234567890"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     assert "Passed" in r.stdout and "AES key expansion took" in r.stdout
+
+
+# ---- AES-192 / AES-256: FIPS-197 Appendix C.2 / C.3 --------------------------------------------------
+@pytest.mark.parametrize("nbytes,want", [(16, "69c4e0d86a7b0430d8cdb78070b4c55a"), (24, "dda97ca4864cdfe06eaf70a0ec0d7191"),
+                                         (32, "8ea2b7ca516745bfeafc49904b496089")])
+def test_aes_192_256_kat(pkg, engine_test, oracle_test, nbytes, want):
+    import aes_clear
+    o = oracle_test
+    key, pt = bytes(range(nbytes)), bytes.fromhex("00112233445566778899aabbccddeeff")
+    rk = engine_test.aes_key_expansion_ex(o.encrypt_bytes(key))
+    assert len(rk) == nbytes // 4 + 7
+    want_rk = aes_clear.round_keys(key)
+    for r in range(len(rk)):
+        assert o.decrypt_bytes(rk[r]) == want_rk[r], f"round key {r}"
+    enc = engine_test.aes_crypt_ex(rk, o.encrypt_bytes(pt)[None])
+    assert o.decrypt_bytes(enc[0]).hex() == want
+    dec = engine_test.aes_crypt_ex(rk, enc, decrypt=True)
+    assert o.decrypt_bytes(dec[0]) == pt

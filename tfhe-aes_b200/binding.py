@@ -54,6 +54,9 @@ _SIGS = {
     "tfa_sbox": [C.c_void_p, C.c_void_p, C.c_int, C.c_int],
     "tfa_many_sbox": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "tfa_aes_key_expansion": [C.c_void_p] * 4,
+    "tfa_aes_key_expansion_ex": [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p],
+    "tfa_aes_encrypt_ex": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int],
+    "tfa_aes_decrypt_ex": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int],
     "tfa_aes_key_expansion_dev": [C.c_void_p] * 4,
     "tfa_aes_encrypt": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int],
     "tfa_aes_decrypt": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int],
@@ -359,6 +362,23 @@ class Engine:
         rc = np.ascontiguousarray(rcon_ct, dtype=np.uint64) if rcon_ct is not None else None
         self._ck(self.lib.tfa_aes_key_expansion(self.h, _p(key_ct), _p(rc), _p(out)))
         return out
+
+    def aes_key_expansion_ex(self, key_ct, rcon_ct=None):
+        """AES-128/192/256: key_ct [16 | 24 | 32][8][lw] -> [11 | 13 | 15][16][8][lw]"""
+        key_ct = np.ascontiguousarray(key_ct, dtype=np.uint64).reshape(-1, 8, self.lw)
+        nb = len(key_ct)
+        out = np.zeros((nb // 4 + 7, 16, 8, self.lw), dtype=np.uint64)
+        rc = np.ascontiguousarray(rcon_ct, dtype=np.uint64) if rcon_ct is not None else None
+        self._ck(self.lib.tfa_aes_key_expansion_ex(self.h, _p(key_ct), nb, _p(rc), _p(out)))
+        return out
+
+    def aes_crypt_ex(self, rk, states, decrypt=False):
+        """rounds follow from the number of round keys (11 / 13 / 15)"""
+        rk = np.ascontiguousarray(rk, dtype=np.uint64).reshape(-1, 16, 8, self.lw)
+        st = np.array(states, dtype=np.uint64).reshape(-1, 16, 8, self.lw)
+        fn = self.lib.tfa_aes_decrypt_ex if decrypt else self.lib.tfa_aes_encrypt_ex
+        self._ck(fn(self.h, _p(rk), _p(st), len(st), len(rk) - 1))
+        return st
 
     def _state_call(self, fn, rk, states):
         rk = np.ascontiguousarray(rk, dtype=np.uint64)

@@ -2,6 +2,8 @@
 // device stages of engine.cu.  Orchestration follows server.rs / sbox.rs line by line; the per-byte
 // loops of the reference (server.rs:47-50, 59-61, 76-78, 88-91, 100-102) become one batched pass
 // over all bytes of all resident blocks.
+#include <chrono>
+#include <condition_variable>
 #include <cstring>
 #include <mutex>
 #include "engine.h"
@@ -242,27 +244,28 @@ static int aes_round_nolock(tfa_ctx *ctx, const u64 *rk_round, u64 *state, int n
     RC(sbox_like_dev(ctx, state, nblk * 16, 1, mul));                      // server.rs:47-50 (many_sbox)
     return lin_mix_columns(ctx, mul, state, rk_round, nblk);               // server.rs:53-55
 }
-static int aes_encrypt_nolock(tfa_ctx *ctx, const u64 *rk, u64 *state, int nblk) {
+// nr = number of rounds: 10 (AES-128, the reference), 12 (AES-192), 14 (AES-256); rk holds nr + 1 round keys
+static int aes_encrypt_nolock(tfa_ctx *ctx, const u64 *rk, u64 *state, int nblk, int nr = 10) {
     const size_t bw = ctx->byte_words(), rkw = 16 * bw;
     WSB(mul, u64, (size_t)nblk * 16 * 3 * bw);
     const size_t mark = ctx->ws_off;
     RC(lin_add_round_key(ctx, state, rk, nblk));                           // server.rs:42
-    for (int round = 1; round < 10; round++) {
+    for (int round = 1; round < nr; round++) {
         ctx->ws_off = mark;
         RC(aes_round_nolock(ctx, rk + (size_t)round * rkw, state, nblk, mul));
     }
     ctx->ws_off = mark;
     RC(sbox_like_dev(ctx, state, nblk * 16, 0, mul));                      // server.rs:59-61
-    return lin_permute_add(ctx, mul, state, rk + 10 * rkw, nblk, 0);       // server.rs:62-63
+    return lin_permute_add(ctx, mul, state, rk + (size_t)nr * rkw, nblk, 0);  // server.rs:62-63
 }
 // Server::aes_decrypt (server.rs:67-105)
-static int aes_decrypt_nolock(tfa_ctx *ctx, const u64 *rk, u64 *state, int nblk) {
+static int aes_decrypt_nolock(tfa_ctx *ctx, const u64 *rk, u64 *state, int nblk, int nr = 10) {
     const size_t bw = ctx->byte_words(), rkw = 16 * bw;
     WSB(mul, u64, (size_t)nblk * 16 * 4 * bw);
     WSB(tmp, u64, (size_t)nblk * 16 * bw);
     const size_t mark = ctx->ws_off;
-    RC(lin_add_round_key(ctx, state, rk + 10 * rkw, nblk));                // server.rs:70
-    for (int round = 10; round >= 2; round--) {
+    RC(lin_add_round_key(ctx, state, rk + (size_t)nr * rkw, nblk));        // server.rs:70
+    for (int round = nr; round >= 2; round--) {
         ctx->ws_off = mark;
         // inv_shift_rows commutes with the byte-wise S-box: S-box first, permutation fused with AddRoundKey
         RC(sbox_like_dev(ctx, state, nblk * 16, 2, mul));                  // server.rs:73-78
@@ -276,11 +279,14 @@ static int aes_decrypt_nolock(tfa_ctx *ctx, const u64 *rk, u64 *state, int nblk)
     return lin_permute_add(ctx, mul, state, rk, nblk, 1);                  // server.rs:98,104
 }
 // Server::aes_key_expansion (server.rs:107-167)
-static int key_expansion_nolock(tfa_ctx *ctx, const u64 *key_ct, const u64 *rcon_ct, u64 *rk) {
+// nk = key words: 4 (AES-128, the reference), 6, 8 (FIPS-197 §5.2); every generated word is refreshed to noise level 1 as
+// server.rs:149-150 does, and the extra SubWord of AES-256 (i mod 8 = 4) goes through the same S-box evaluation
+static int key_expansion_nolock(tfa_ctx *ctx, const u64 *key_ct, const u64 *rcon_ct, u64 *rk, int nk = 4) {
     static const uint8_t RCON[10] = {0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, 0x1B, 0x36};  // key_expansion_utils.rs:10-12
     const size_t bw = ctx->byte_words();
     const int lw = ctx->lw;
-    CU(cudaMemcpyAsync(rk, key_ct, 16 * bw * 8, cudaMemcpyDeviceToDevice, ctx->stream));  // server.rs:122-128
+    const int nwords = 4 * (nk + 6 + 1);
+    CU(cudaMemcpyAsync(rk, key_ct, (size_t)4 * nk * bw * 8, cudaMemcpyDeviceToDevice, ctx->stream));  // server.rs:122-128
     WSB(rcon, u64, 10 * bw);
     if (rcon_ct) CU(cudaMemcpyAsync(rcon, rcon_ct, 10 * bw * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     else {
@@ -292,22 +298,28 @@ static int key_expansion_nolock(tfa_ctx *ctx, const u64 *key_ct, const u64 *rcon
     WSB(temp, u64, 4 * bw); WSB(sub, u64, 4 * bw); WSB(sum, u64, 4 * bw);
     const size_t mark = ctx->ws_off;
     auto W = [&](int i, int j) { return rk + ((size_t)i * 4 + j) * bw; };  // word i, byte j (flat = round-key layout)
-    for (int i = 4; i < 44; i++) {
+    for (int i = nk; i < nwords; i++) {
         ctx->ws_off = mark;
         const u64 *t[4];
-        if (i % 4 == 0) {
+        if (nk > 6 && i % nk == 4) {
+            std::vector<SumEntry> v;  // AES-256 only: temp = SubWord(w[i-1])
+            for (int j = 0; j < 4; j++) v.push_back(entry(temp + (size_t)j * bw, {W(i - 1, j)}));
+            RC(dev_lwe_sum(ctx, v, (int)bw));
+            RC(sbox_like_dev(ctx, temp, 4, 0, sub));
+            for (int j = 0; j < 4; j++) t[j] = sub + (size_t)j * bw;
+        } else if (i % nk == 0) {
             std::vector<SumEntry> v;  // fhe_rot_word: temp[j] = w[i-1][(j+1)%4]
             for (int j = 0; j < 4; j++) v.push_back(entry(temp + (size_t)j * bw, {W(i - 1, (j + 1) % 4)}));
             RC(dev_lwe_sum(ctx, v, (int)bw));
             RC(sbox_like_dev(ctx, temp, 4, 0, sub));                        // fhe_sub_word
-            std::vector<SumEntry> a{entry(sub, {sub, rcon + (size_t)(i / 4 - 1) * bw})};  // server.rs:143
+            std::vector<SumEntry> a{entry(sub, {sub, rcon + (size_t)(i / nk - 1) * bw})};  // server.rs:143
             RC(dev_lwe_sum(ctx, a, (int)bw));
             for (int j = 0; j < 4; j++) t[j] = sub + (size_t)j * bw;
         } else {
             for (int j = 0; j < 4; j++) t[j] = W(i - 1, j);
         }
         std::vector<SumEntry> v;
-        for (int j = 0; j < 4; j++) v.push_back(entry(sum + (size_t)j * bw, {W(i - 4, j), t[j]}));  // server.rs:148
+        for (int j = 0; j < 4; j++) v.push_back(entry(sum + (size_t)j * bw, {W(i - nk, j), t[j]}));  // server.rs:148
         RC(dev_lwe_sum(ctx, v, (int)bw));
         RC(sbox_like_dev(ctx, sum, 4, 4, W(i, 0)));                         // refresh, server.rs:150
     }
@@ -471,24 +483,102 @@ extern "C" int tfa_aes_ctr_dev(tfa_ctx *ctx, const uint64_t *rk, const uint64_t 
 }
 
 // ---- host-pointer entry points ---------------------------------------------------------------------
-#define HOST_STATE_CALL(scratch, body)                                                         \
-    Guard g(ctx);                                                                              \
-    if (nblk < 1) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1");                        \
-    RC(require_keys(ctx));                                                                     \
-    const size_t sw = (size_t)nblk * 16 * ctx->byte_words(), rkw = (size_t)11 * 16 * ctx->byte_words(); \
-    RC(ws_reserve(ctx, (scratch) + (sw + rkw) * 8));                                           \
-    WSB(d_rk, u64, rkw); WSB(d_st, u64, sw);                                                   \
-    H2D(d_rk, round_keys, rkw); H2D(d_st, states, sw);                                         \
-    RC(body);                                                                                  \
-    D2H(states, d_st, sw);                                                                     \
-    SYNC();                                                                                    \
-    return TFA_OK
+// ---- request coalescing ------------------------------------------------------------------------------
+// The reference calls add_scalar + aes_encrypt once per block from rayon workers that share one &Server (main.rs:55-64).
+// One block exposes 128 bootstraps per round, a B200 wants 444 per wave of the PBS kernel, so concurrent per-block calls
+// are merged: every caller queues its request; the first one becomes the leader, lingers a fraction of a millisecond while
+// further callers arrive, runs all compatible requests (same operation, same round keys) as ONE batch and wakes the others.
+// Blocks are independent, so each caller gets exactly what its own call would have produced.
+enum { OP_ENCRYPT = 0, OP_DECRYPT = 1, OP_ADD_SCALAR = 2 };
+struct CoalesceReq {
+    int op;
+    const u64 *rk;
+    u64 *states;
+    const u64 *counters;
+    int nblk;
+    int rc;
+    bool done;
+};
+// round keys of two callers: the same buffer, or equal on 1 024 words sampled across the 23 MB (every caller of the Rust shim
+// flattens its own copy; honest ciphertexts that agree on 1 024 random-looking words are the same ciphertexts)
+static bool same_round_keys(const tfa_ctx *ctx, const u64 *a, const u64 *b) {
+    if (a == b) return true;
+    const size_t rkw = (size_t)11 * 16 * ctx->byte_words(), stride = rkw / 1024;
+    for (size_t i = 0; i < 1024; i++)
+        if (a[i * stride + (i & 7)] != b[i * stride + (i & 7)]) return false;
+    return true;
+}
+static int run_batch(tfa_ctx *ctx, const std::vector<CoalesceReq *> &batch) {
+    Guard g(ctx);
+    RC(require_keys(ctx));
+    int nblk = 0;
+    for (auto r : batch) nblk += r->nblk;
+    const int op = batch[0]->op;
+    const size_t bw = ctx->byte_words(), sw = (size_t)nblk * 16 * bw, rkw = (size_t)11 * 16 * bw;
+    const size_t scratch = op == OP_ADD_SCALAR ? add_scalar_scratch(ctx, nblk) + (size_t)nblk * 16 : aes_scratch(ctx, nblk, op == OP_ENCRYPT ? 3 : 5) + rkw * 8;
+    RC(ws_reserve(ctx, scratch + sw * 8));
+    WSB(d_st, u64, sw);
+    size_t off = 0;
+    for (auto r : batch) { H2D(d_st + off, r->states, (size_t)r->nblk * 16 * bw); off += (size_t)r->nblk * 16 * bw; }
+    if (op == OP_ADD_SCALAR) {
+        WSB(d_ctr, u64, (size_t)nblk * 2);
+        size_t c = 0;
+        for (auto r : batch) { H2D(d_ctr + c, r->counters, (size_t)r->nblk * 2); c += (size_t)r->nblk * 2; }
+        RC(add_scalar_nolock(ctx, d_st, d_ctr, nblk));
+    } else {
+        WSB(d_rk, u64, rkw);
+        H2D(d_rk, batch[0]->rk, rkw);
+        if (op == OP_ENCRYPT) RC(aes_encrypt_nolock(ctx, d_rk, d_st, nblk));
+        else RC(aes_decrypt_nolock(ctx, d_rk, d_st, nblk));
+    }
+    off = 0;
+    for (auto r : batch) { D2H(r->states, d_st + off, (size_t)r->nblk * 16 * bw); off += (size_t)r->nblk * 16 * bw; }
+    SYNC();
+    return TFA_OK;
+}
+static int coalesced_call(tfa_ctx *ctx, int op, const u64 *rk, u64 *states, const u64 *counters, int nblk) {
+    if (nblk < 1 || !states || (op == OP_ADD_SCALAR ? !counters : !rk)) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1 and the pointers non-null");
+    CoalesceReq me{op, rk, states, counters, nblk, TFA_OK, false};
+    std::unique_lock<std::mutex> ql(ctx->qmu);
+    ctx->queue.push_back(&me);
+    ctx->qcv.notify_all();                                  // a lingering leader sees the arrival
+    while (!me.done && ctx->leader) ctx->qcv.wait(ql);
+    if (me.done) return me.rc;
+    ctx->leader = true;
+    while (!me.done) {
+        // linger until no caller has arrived for 1 ms (at most 16 ms; the shortest AES call takes 200 ms at PARAM_OPT): threads
+        // released together by the previous batch come back within a fraction of a millisecond of each other
+        size_t seen = ctx->queue.size();
+        for (int spin = 0; spin < 16; spin++) {
+            ctx->qcv.wait_for(ql, std::chrono::microseconds(1000));
+            if (ctx->queue.size() == seen) break;
+            seen = ctx->queue.size();
+        }
+        // the batch: every queued request compatible with the oldest one, up to 1 024 blocks
+        std::vector<CoalesceReq *> batch, rest;
+        CoalesceReq *head = ctx->queue.front();
+        int blocks = 0;
+        for (auto r : ctx->queue) {
+            const bool ok = r == head || (r->op == head->op && blocks + r->nblk <= 1024 && (head->op == OP_ADD_SCALAR || same_round_keys(ctx, head->rk, r->rk)));
+            if (ok) { batch.push_back(r); blocks += r->nblk; } else rest.push_back(r);
+        }
+        ctx->queue.swap(rest);
+        ql.unlock();
+        const int rc = run_batch(ctx, batch);
+        ql.lock();
+        for (auto r : batch) { r->rc = rc; r->done = true; }
+        ctx->qcv.notify_all();
+    }
+    ctx->leader = false;                                    // whoever is still queued elects the next leader
+    ctx->qcv.notify_all();
+    return me.rc;
+}
 
 extern "C" int tfa_aes_encrypt(tfa_ctx *ctx, const uint64_t *round_keys, uint64_t *states, int nblk) {
-    HOST_STATE_CALL(aes_scratch(ctx, nblk, 3), aes_encrypt_nolock(ctx, d_rk, d_st, nblk));
+    return coalesced_call(ctx, OP_ENCRYPT, round_keys, states, nullptr, nblk);
 }
 extern "C" int tfa_aes_decrypt(tfa_ctx *ctx, const uint64_t *round_keys, uint64_t *states, int nblk) {
-    HOST_STATE_CALL(aes_scratch(ctx, nblk, 5), aes_decrypt_nolock(ctx, d_rk, d_st, nblk));
+    return coalesced_call(ctx, OP_DECRYPT, round_keys, states, nullptr, nblk);
 }
 extern "C" int tfa_aes_encryption(tfa_ctx *ctx, const uint64_t *rk, uint64_t *st, int nblk) { return tfa_aes_encrypt(ctx, rk, st, nblk); }
 extern "C" int tfa_aes_decryption(tfa_ctx *ctx, const uint64_t *rk, uint64_t *st, int nblk) { return tfa_aes_decrypt(ctx, rk, st, nblk); }
@@ -506,32 +596,50 @@ extern "C" int tfa_aes_round(tfa_ctx *ctx, const uint64_t *round_key, uint64_t *
     SYNC();
     return TFA_OK;
 }
-extern "C" int tfa_aes_key_expansion(tfa_ctx *ctx, const uint64_t *key_ct, const uint64_t *rcon_ct, uint64_t *rk_out) {
+// AES-128 / 192 / 256: key_bytes = 16, 24 or 32; rk_out holds key_bytes / 4 + 7 round keys
+extern "C" int tfa_aes_key_expansion_ex(tfa_ctx *ctx, const uint64_t *key_ct, int key_bytes, const uint64_t *rcon_ct, uint64_t *rk_out) {
     Guard g(ctx);
     RC(require_keys(ctx));
+    if (key_bytes != 16 && key_bytes != 24 && key_bytes != 32) return ctx->fail(TFA_ERR_PARAM, "key_bytes must be 16, 24 or 32");
+    const int nk = key_bytes / 4, nrk = nk + 7;
     const size_t bw = ctx->byte_words();
-    RC(ws_reserve(ctx, aes_scratch(ctx, 1, 1) + (16 + 10 + 176 + 32) * bw * 8));
-    WSB(d_key, u64, 16 * bw); WSB(d_rk, u64, 176 * bw);
+    RC(ws_reserve(ctx, aes_scratch(ctx, 1, 1) + ((size_t)key_bytes + 10 + 16 * nrk + 32) * bw * 8));
+    WSB(d_key, u64, (size_t)key_bytes * bw); WSB(d_rk, u64, (size_t)16 * nrk * bw);
     u64 *d_rcon = nullptr;
-    H2D(d_key, key_ct, 16 * bw);
+    H2D(d_key, key_ct, (size_t)key_bytes * bw);
     if (rcon_ct) { d_rcon = ws_get<u64>(ctx, 10 * bw); if (!d_rcon) return TFA_ERR_STATE; H2D(d_rcon, rcon_ct, 10 * bw); }
-    RC(key_expansion_nolock(ctx, d_key, d_rcon, d_rk));
-    D2H(rk_out, d_rk, 176 * bw);
+    RC(key_expansion_nolock(ctx, d_key, d_rcon, d_rk, nk));
+    D2H(rk_out, d_rk, (size_t)16 * nrk * bw);
     SYNC();
     return TFA_OK;
 }
-extern "C" int tfa_add_scalar(tfa_ctx *ctx, uint64_t *states, const uint64_t *counters, int nblk) {
+extern "C" int tfa_aes_key_expansion(tfa_ctx *ctx, const uint64_t *key_ct, const uint64_t *rcon_ct, uint64_t *rk_out) {
+    return tfa_aes_key_expansion_ex(ctx, key_ct, 16, rcon_ct, rk_out);
+}
+// rounds = 10, 12 or 14; round_keys [rounds + 1][16][8][lw]; states in place
+static int aes_crypt_ex(tfa_ctx *ctx, const uint64_t *round_keys, uint64_t *states, int nblk, int rounds, bool decrypt) {
     Guard g(ctx);
-    if (nblk < 1) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1");
+    if (nblk < 1 || !round_keys || !states) return ctx->fail(TFA_ERR_PARAM, "nblk must be >= 1 and the pointers non-null");
+    if (rounds != 10 && rounds != 12 && rounds != 14) return ctx->fail(TFA_ERR_PARAM, "rounds must be 10, 12 or 14");
     RC(require_keys(ctx));
-    const size_t sw = (size_t)nblk * 16 * ctx->byte_words();
-    RC(ws_reserve(ctx, add_scalar_scratch(ctx, nblk) + sw * 8 + (size_t)nblk * 16));
-    WSB(d_st, u64, sw); WSB(d_ctr, u64, (size_t)nblk * 2);
-    H2D(d_st, states, sw); H2D(d_ctr, counters, (size_t)nblk * 2);
-    RC(add_scalar_nolock(ctx, d_st, d_ctr, nblk));
+    const size_t sw = (size_t)nblk * 16 * ctx->byte_words(), rkw = (size_t)(rounds + 1) * 16 * ctx->byte_words();
+    RC(ws_reserve(ctx, aes_scratch(ctx, nblk, decrypt ? 5 : 3) + (sw + rkw) * 8));
+    WSB(d_rk, u64, rkw); WSB(d_st, u64, sw);
+    H2D(d_rk, round_keys, rkw); H2D(d_st, states, sw);
+    if (decrypt) RC(aes_decrypt_nolock(ctx, d_rk, d_st, nblk, rounds));
+    else RC(aes_encrypt_nolock(ctx, d_rk, d_st, nblk, rounds));
     D2H(states, d_st, sw);
     SYNC();
     return TFA_OK;
+}
+extern "C" int tfa_aes_encrypt_ex(tfa_ctx *ctx, const uint64_t *round_keys, uint64_t *states, int nblk, int rounds) {
+    return aes_crypt_ex(ctx, round_keys, states, nblk, rounds, false);
+}
+extern "C" int tfa_aes_decrypt_ex(tfa_ctx *ctx, const uint64_t *round_keys, uint64_t *states, int nblk, int rounds) {
+    return aes_crypt_ex(ctx, round_keys, states, nblk, rounds, true);
+}
+extern "C" int tfa_add_scalar(tfa_ctx *ctx, uint64_t *states, const uint64_t *counters, int nblk) {
+    return coalesced_call(ctx, OP_ADD_SCALAR, nullptr, states, counters, nblk);
 }
 extern "C" int tfa_aes_ctr(tfa_ctx *ctx, const uint64_t *round_keys, const uint64_t *iv_ct, uint64_t first_lo, uint64_t first_hi, int nblk, uint64_t *out) {
     Guard g(ctx);

@@ -1,6 +1,7 @@
 // engine.h — internal context of the library (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -44,6 +45,12 @@ struct tfa_ctx {
     int pbs_schedule;      // 0 auto, 1 phase-synchronous, 2 warp-specialised (tfa_ctx_set_pbs_schedule)
     struct ProfRec { int stage; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
+
+    // request coalescing of the per-block host entry points (api.cu): callers queue here, one of them runs the batch
+    std::mutex qmu;
+    std::condition_variable qcv;
+    std::vector<struct CoalesceReq *> queue;
+    bool leader = false;
 
     // bump workspace
     char *ws;
