@@ -120,7 +120,7 @@ extern "C" void tfa_ctx_destroy(tfa_ctx *ctx) {
 extern "C" const char *tfa_last_error(const tfa_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 extern "C" int tfa_ctx_synchronize(tfa_ctx *ctx) { CU(cudaStreamSynchronize(ctx->stream)); return TFA_OK; }
 extern "C" int tfa_ctx_set_pbs_schedule(tfa_ctx *ctx, int schedule) {
-    if (schedule < 0 || schedule > 2) return ctx->fail(TFA_ERR_PARAM, "pbs schedule must be 0 (auto), 1 (phase-synchronous) or 2 (warp-specialised)");
+    if (schedule < 0 || schedule > 3) return ctx->fail(TFA_ERR_PARAM, "pbs schedule must be 0 (auto), 1 (phase-synchronous), 2 (warp-specialised) or 3 (one PBS per two-CTA cluster)");
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->pbs_schedule = schedule;
     return TFA_OK;
@@ -307,6 +307,31 @@ int dev_pbs(tfa_ctx *ctx, const u64 *in, int count, const u64 *lut, u64 in_scale
     //   phase-synchronous (fp_kernels.cu):   13.1 ms at G = 3
     // The warp-specialised kernel is the default wherever it is instantiated; the phase-synchronous one serves the
     // remaining shapes (K = 1 test parameter sets with G > 1) and stays selectable for comparison.
+    // Small batches (at most one wave of two-CTA clusters, 74 ciphertexts): one PBS per cluster, levels transformed in parallel
+    // (pbs_cl2_kernel.cu) -- key expansion stages, carry chain of few blocks, a single CTR block.
+    static const bool no_cluster = getenv("TFA_PBS_NO_CLUSTER") != nullptr;
+    if (ctx->k == 4 && ((ctx->pbs_schedule == 0 && count <= 74 && !no_cluster) || ctx->pbs_schedule == 3)) {
+        if (getenv("TFA_PBS_TIMING")) {   // debug aid: per-activity cycles of cluster 0 / CTA 0 (FFT thread 0, MAC thread 0)
+            uint64_t *d = nullptr, h[12];
+            CU(cudaMalloc(&d, sizeof(h)));
+            CU(cudaMemsetAsync(d, 0, sizeof(h), ctx->stream));
+            a.dbg = d;
+            CU(launch_pbs_cl2(a, ctx->stream));
+            CU(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            cudaFree(d);
+            static const char *nm[12] = {"F:wait_acc", "F:decompose", "F:fwd_fft", "F:cluster_bar", "F:wait_inv", "F:inverse",
+                                         "M:wait_row", "M:row", "M:remote_store", "M:cluster_bar", "M:sum+handover", "-"};
+            fprintf(stderr, "[pbs_cl2 timing] cycles per CMux step:");
+            for (int k = 0; k < 11; k++) fprintf(stderr, " %s=%.0f", nm[k], (double)h[k] / ctx->n);
+            fprintf(stderr, "\n");
+            ctx->launches++;
+            return TFA_OK;
+        }
+        CU(launch_pbs_cl2(a, ctx->stream));
+        ctx->launches++;
+        return TFA_OK;
+    }
     const int G = pick_G(ctx->k, count);
     static const bool timing = getenv("TFA_PBS_TIMING") != nullptr;
     const bool ws_available = true;   // every (K, G) pick_G returns is instantiated in both kernels
