@@ -35,7 +35,7 @@ struct ClSmem {
     cd rx[2][CL_MAXP][POLY_M];                  // partial sums of own columns from the peer CTA, double-buffered by step parity
     cd tw[256];
     uint64_t allspec;                           // every spectrum of the step is in its slot (FFT groups -> MAC role)
-    uint64_t rxfull;                            // the peer's partial sums of the step have landed in rx (peer MAC warps -> MAC role), cluster scope
+    uint64_t rxfull;                            // the peer's partial sums of the step have landed in rx (byte count of its st.async stores)
     uint64_t inv;                               // Fourier sums of the own columns in slots 0..np-1 (MAC role -> owner groups)
     uint64_t accready[CL_MAXP];                 // polynomial updated (owner group -> the 5 groups of that polynomial)
 };
@@ -49,8 +49,12 @@ __device__ __forceinline__ unsigned map_to_peer(const void *local_addr, unsigned
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(peer));
     return ra;
 }
-__device__ __forceinline__ void st_cluster_cd(unsigned remote_addr, cd v) {
-    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(remote_addr), "d"(v.x), "d"(v.y) : "memory");
+// asynchronous remote store: the 16 bytes are counted on the receiver's mbarrier when they land (no release fence, the sender
+// does not wait for the round trip)
+__device__ __forceinline__ void st_async_cd(unsigned remote_addr, cd v, unsigned remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(remote_addr), "d"(v.x), "d"(v.y),
+                 "r"(remote_bar)
+                 : "memory");
 }
 // arrive on the peer's barrier; release at cluster scope orders this thread's (and, after __syncwarp, its warp's) remote stores before it
 __device__ __forceinline__ void mbar_arrive_remote(unsigned remote_bar) {
@@ -212,14 +216,14 @@ __device__ __forceinline__ void cl2_body(const PbsArgs &a, ClSmem &sm, const uns
                     for (int c = 0; c <= CL_K; c++) wbuf[r][c] = t[r][c];
             }
             CT(1);
-            // partial sums of the peer's columns -> its shared memory, then one arrival per warp on its rxfull barrier
+            // partial sums of the peer's columns -> its shared memory; the bytes complete its rxfull barrier as they land
 #pragma unroll
             for (int c = 0; c < PEER_NP; c++)
-                st_cluster_cd(remote_rx + (unsigned)(((i & 1) * CL_MAXP + c) * POLY_M * sizeof(cd)), facc[peer_pbase + c]);
-            __syncwarp();
-            if (mlane == 0) mbar_arrive_remote(remote_bar);
+                st_async_cd(remote_rx + (unsigned)(((i & 1) * CL_MAXP + c) * POLY_M * sizeof(cd)), facc[peer_pbase + c], remote_bar);
             CT(2);
             mbar_wait_cluster(&sm.rxfull, (unsigned)i & 1);
+            // the next phase expects the peer's NP columns again (posted thousands of cycles before the peer can send them)
+            if (p == 0) ws_mbar_arrive_expect_tx(&sm.rxfull, (unsigned)(NP * POLY_M * sizeof(cd)));
             CT(3);
 #pragma unroll
             for (int c = 0; c < NP; c++) {
@@ -247,7 +251,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) pbs_cl2_kernel(PbsArgs a) {
     for (int i = tid; i < 256; i += CL_THREADS) sm.tw[i] = a.tw[i];
     if (tid == 0) {
         ws_mbar_init(&sm.allspec, np * CL_LEVELS);
-        ws_mbar_init(&sm.rxfull, CL_MAC_WARPS);
+        ws_mbar_init(&sm.rxfull, 1);
+        ws_mbar_arrive_expect_tx(&sm.rxfull, (unsigned)(np * POLY_M * sizeof(cd)));   // step 0: np columns of 4 KB from the peer
         ws_mbar_init(&sm.inv, CL_MAC_WARPS);
         for (int lp = 0; lp < CL_MAXP; lp++) ws_mbar_init(&sm.accready[lp], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
