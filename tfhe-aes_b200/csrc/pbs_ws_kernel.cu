@@ -34,7 +34,7 @@
 #define PBS_WS_LAUNCH_NAME launch_pbs_ws
 #endif
 // Tuning switches.  The defaults are the configuration measured best on B200 with scratch/pbs_lab (one wave of 444 ciphertexts,
-// every variant checked bit for bit against the round-1 kernel): 10.41 ms against 10.59 ms.  DESIGN.md §7 lists what was measured
+// every variant checked bit for bit against the round-1 kernel): 10.12 ms against 10.59 ms.  DESIGN.md §7 lists what was measured
 // for each of them and for the schedules that lost (row-ahead barrier probes, software-pipelined MAC rows, twiddles on the pass-2 side).
 #ifndef WS_MAC_REUSE
 #define WS_MAC_REUSE 1    // FMAs of one key value ordered so that consecutive DFMAs share an operand (a DFMA with three distinct
@@ -48,6 +48,9 @@
 #ifndef WS_ROT_LATE
 #define WS_ROT_LATE 1     // the next mask element is fetched before the inverse FFT and mod-switched after it
 #endif
+#ifndef WS_TMEM_ST
+#define WS_TMEM_ST 1      // the digits of the levels still to come are parked in tensor memory (tcgen05.st / tcgen05.ld, 32 columns per thread)
+#endif                    // instead of 32 registers per FFT thread: no spills, and ptxas keeps several twiddle loads in flight (10.40 -> 10.12 ms)
 #ifndef WS_DIAG
 #define WS_DIAG 0         // diagnostics of scratch/pbs_lab: each bit removes one piece of work (results are WRONG when != 0)
 #endif
@@ -64,7 +67,8 @@ struct WsSmem {
     uint64_t bfull[2];                   // key rows 0..BSPLIT-1 / BSPLIT..K of a level have landed
     uint64_t bempty[K + 1];
     uint64_t inv;
-    uint64_t pad_;
+    uint32_t tmem_base;                  // WS_TMEM_ST: base address of the allocated tensor-memory columns
+    uint32_t pad_;
 };
 
 // facc[g][c] += x[g] * w for all g, in an order that lets consecutive DFMAs share the key component as one operand: a DFMA with
@@ -125,6 +129,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
         ws_mbar_init(&sm.inv, WS_MAC_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+#if WS_TMEM_ST
+    if (tid < 32) {   // warp 0: 64 columns = 32 per FFT warp, two FFT warps per lane quarter
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(ws_smem_u32(&sm.tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#endif
     for (int g = 0; g < G; g++) {
         const int rot = (2 * POLY_N - ws_mod_switch_2n(a, min(ct0 + g, a.count - 1), n)) & (2 * POLY_N - 1);
         for (int idx = tid; idx < (K + 1) * POLY_N; idx += WS_THREADS) {
@@ -142,7 +153,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
 #endif
     if (WS_FFT_HIGH ? (tid >= WS_THREADS - WS_FFT_THREADS) : (tid < WS_FFT_THREADS)) {
         // ================================ FFT warps ================================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(256 - MAC_REGS));
+        if (MAC_REGS <= 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(256 - MAC_REGS));
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(256 - MAC_REGS));
         const int ftid = WS_FFT_HIGH ? tid - (WS_THREADS - WS_FFT_THREADS) : tid;
 #if WS_REVMAP   // groups in reverse warp order: the issue arbiter favours high warp ids, and the MAC role consumes row 0 first
         const int gid = 15 - (ftid >> 4), lane = ftid & 15;
@@ -167,6 +179,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
         const int my_ct = min(ct0 + ct, a.count - 1);
         cd v[16];
         uint32_t st_re[16], st_im[16];
+#if WS_TMEM_ST
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // this warp's lane quarter is (tid / 32) % 4; the two FFT warps that share a quarter use columns 0..31 / 32..63
+        const unsigned taddr = sm.tmem_base + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)((ftid >> 7) * 32);
+#endif
         unsigned produced = 0;                    // levels this group has produced so far
         if (gid_a < G * (K + 1)) {
             int rot = ws_mod_switch_2n(a, my_ct, 0);
@@ -178,13 +195,36 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
 #endif
                 if (TIMING) { trace_on = blockIdx.x == 0 && (ftid == 0 || ftid == 224) && i >= 100 && i < 104; trace_sec = ftid == 0 ? 0 : 1; }
                 load_decompose_rot<BASE_LOG, LEVELS>(sm.acc[ct][r], lane, rot, v, st_re, st_im);
+#if WS_TMEM_ST
+                // park the digits of levels 4..1: per level one word per four coefficients (8 words), 32 columns per thread
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        pk[j] = ws_gather_byte(st_re[4 * j], st_re[4 * j + 1], st_re[4 * j + 2], st_re[4 * j + 3], b);
+                        pk[4 + j] = ws_gather_byte(st_im[4 * j], st_im[4 * j + 1], st_im[4 * j + 2], st_im[4 * j + 3], b);
+                    }
+                    ws_tmem_st8(taddr + b * 8, pk);
+                }
+                ws_tmem_wait_st();
+#endif
 #if !WS_ROT_LATE
                 rot = rot_next;
 #endif
                 WT(WT_F_DECOMP);
 #pragma unroll 1
                 for (int lev = LEVELS; lev >= 1; lev--) {
+#if WS_TMEM_ST
+                    if (lev != LEVELS) {
+                        uint32_t pk[8];
+                        ws_tmem_ld8(taddr + (4 - lev) * 8, pk);
+#pragma unroll
+                        for (int n1 = 0; n1 < 16; n1++) v[n1] = cmk(digit85(pk[n1 >> 2], n1 & 3), digit85(pk[4 + (n1 >> 2)], n1 & 3));
+                    }
+#else
                     if (lev != LEVELS) next_digits<BASE_LOG, LEVELS>(v, st_re, st_im, lev);
+#endif
                     // first pass in registers; only then wait until the MAC warps have consumed the previous
                     // occupant of the slot (rows of the previous production)
 #if WS_DIAG & 64           // diagnostic (wrong results): no first-pass arithmetic
@@ -261,7 +301,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
         }
     } else {
         // ================================ MAC warps ================================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MAC_REGS));
+        if (MAC_REGS <= 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MAC_REGS));
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MAC_REGS));
         const int p = WS_FFT_HIGH ? tid : tid - WS_FFT_THREADS;
         const int mwarp = p >> 5, mlane = p & 31;
         auto produce = [&](int q) {               // fetch key row q into slot q % RING (the caller knows it is free)
@@ -364,6 +405,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
     }
 #undef WT
     __syncthreads();
+#if WS_TMEM_ST
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(sm.tmem_base) : "memory");
+#endif
     // sample extract of coefficient 0
     for (int g = 0; g < G; g++) {
         if (ct0 + g >= a.count) continue;

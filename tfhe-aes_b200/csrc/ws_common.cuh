@@ -59,6 +59,26 @@ __device__ __forceinline__ void ws_mbar_wait_lane(uint64_t *bar, unsigned parity
         "WAITL_DONE:\n\t}" ::"r"(ws_smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// ---- tensor memory as a parking lot for per-thread state (32x32b shape: thread t of a warp owns TMEM lane 32 * (warp % 4) + t) ----
+__device__ __forceinline__ void ws_tmem_st8(unsigned taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ws_tmem_ld8(unsigned taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void ws_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// byte b of four words -> one word (digits of one decomposition level of four coefficients)
+__device__ __forceinline__ uint32_t ws_gather_byte(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, int b) {
+    const uint32_t lo = __byte_perm(w0, w1, 0x0040 + b * 0x11);   // bytes: w0[b], w1[b]
+    const uint32_t hi = __byte_perm(w2, w3, 0x0040 + b * 0x11);
+    return __byte_perm(lo, hi, 0x5410);
+}
+
 // modulus switch to 2N: a~ = (a * in_scale [+ pre_add on the body] + 2^53) >> 54
 __device__ __forceinline__ int ws_mod_switch_2n(const PbsArgs &a, int ct, int i) {
     uint64_t x = a.lwe_in[(size_t)ct * (a.lwe_dim + 1) + i] * a.in_scale;
