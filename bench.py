@@ -36,7 +36,7 @@ def pbs_per_block(blocks):       # batched tfa_aes_ctr: IV bits bootstrapped onc
 
 
 BSK_BYTES = 342_528_000
-NCU_DRAM_BYTES_PER_WAVE = 350_468_864   # ncu --set full, pbs_ws_kernel<4,3,8,5>, 148 CTAs x 3 ciphertexts (profiles/r1_pbs_ws_kernel_ncu.txt)
+NCU_DRAM_BYTES_PER_WAVE = 352_174_592   # ncu --set full, pbs_ws_kernel<4,3,8,5>, 148 CTAs x 3 ciphertexts (profiles/r2_pbs_ws_kernel_ncu.txt: 347.35 MB read + 4.82 MB written)
 METRIC = "aes128_ctr_blocks_per_s"
 UNIT = "blocks/s"
 
@@ -430,7 +430,7 @@ def run_gpu(args):
             "roofline": {"bound": "fp64", "kernel": "pbs_ws_kernel<4,3,8,5>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
                          "peak_source": "max of the DFMA and the mma.sync.m8n8k4.f64 microbenchmarks of the FP64 pipe in this run (MEASURED_PEAKS.json has no FP64 figure)",
                          "peak_dfma": peak_dfma, "peak_dmma": peak_dmma, "traffic": NCU_DRAM_BYTES_PER_WAVE * -(-count // 444),
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one 444-PBS wave (profiles/r1_pbs_ws_kernel_ncu.txt: 346.2 + 4.2 MB) x waves in this launch; algorithmic = 342.5 MB of key per wave",
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one 444-PBS wave (profiles/r2_pbs_ws_kernel_ncu.txt: 347.4 + 4.8 MB) x waves in this launch; algorithmic = 342.5 MB of key per wave",
                          "launch_ms": pbs_ms, "pbs_per_launch": count, "flop_per_pbs": PBS_FLOP,
                          "bsk_hbm_gbs": BSK_BYTES * -(-count // (3 * 148)) / (pbs_ms * 1e-3) * 1e-9, "hbm_peak_gbs": hbm,
                          "note": "the key (342.5 MB) is read from HBM once per wave of 444 PBS and served from L2 to the other CTAs"},
