@@ -91,3 +91,33 @@ def test_client_generator_is_chacha20(pkg):
     stream = b"".join(int(v).to_bytes(8, "little") for v in out)
     assert stream.hex() == ("10f1e7e4d13b5915500fdd1fa32071c4c7d1f4c733c068030422aa9ac3d46c4e"
                             "d2826446079faa0914c2d705d98b02a2b5129cd1de164eb9cbd083e8a2503c4e")
+
+
+def test_rust_shim_binds_only_declared_symbols(pkg):
+    """rust/src/ffi.rs (the shim a maintainer compiles against tfhe-rs, which cannot be built in this image) declares exactly
+    entry points that the header declares and the library exports, with matching argument counts."""
+    ffi = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "tfhe_aes_b200.h")).read(), flags=re.S)
+    lib = pkg.load_library()
+    decls = re.findall(r"pub fn (tfa_[a-z0-9_]+)\((.*?)\)", ffi, flags=re.S)
+    assert len(decls) >= 12
+    for name, args in decls:
+        assert hasattr(lib, name), name
+        m = re.search(r"\b%s\s*\((.*?)\)\s*;" % name, hdr, flags=re.S)
+        assert m, f"{name} is not declared in the header"
+        n_rust = len([a for a in args.split(",") if a.strip()])
+        n_c = len([a for a in m.group(1).split(",") if a.strip() and a.strip() != "void"])
+        assert n_rust == n_c, (name, n_rust, n_c)
+    # the reference's surface is all there (server.rs:32,39,67,107,172; sbox.rs:46,68; many_wopbs.rs:31; gen_lut.rs:9)
+    srv = open(os.path.join(ROOT, "rust", "src", "server.rs")).read()
+    for sig in ("pub fn new(public_key: PublicKey, sks: ServerKey, wopbs_key: WopbsKey) -> Self", "pub fn aes_encrypt(&self,", "pub fn aes_decrypt(&self,",
+                "pub fn aes_key_expansion(&self,", "pub fn add_scalar(&self,"):
+        assert sig in srv, sig
+    sb = open(os.path.join(ROOT, "rust", "src", "sbox.rs")).read()
+    for sig in ("pub fn gen_lut<F>(message_mod: usize, carry_mod: usize, poly_size: usize, nb_block: usize, f: F) -> IntegerWopbsLUT",
+                "pub fn many_wopbs_without_padding(ct_in: &mut BaseRadixCiphertext<Ciphertext>, wopbs_key_short: &WopbsKey, luts: Vec<IntegerWopbsLUT>)",
+                "pub fn sbox(", "pub fn many_sbox(wopbs_key_short: &WopbsKey, ct_in: &mut BaseRadixCiphertext<Ciphertext>, inv: bool)"):
+        assert sig in sb, sig
+    for f in ("Cargo.toml", "build.rs", "README.md", "src/lib.rs", "src/flatten.rs", "tests/parity.rs"):
+        assert os.path.exists(os.path.join(ROOT, "rust", f)), f
+    assert "unimplemented!" not in srv + sb + open(os.path.join(ROOT, "rust", "src", "flatten.rs")).read()

@@ -25,7 +25,10 @@ constexpr int CL_K = 4;
 constexpr int CL_LEVELS = 5;
 constexpr int CL_MAXP = 3;                      // polynomials of CTA 0 (CTA 1 has 2)
 constexpr int CL_ROWS = CL_MAXP * CL_LEVELS;    // 15 (level, polynomial) pairs / key rows per step in CTA 0
-constexpr int CL_PF = 4;                        // key rows in flight per MAC thread (registers)
+#ifndef CL_PF_ROWS
+#define CL_PF_ROWS 5
+#endif
+constexpr int CL_PF = CL_PF_ROWS;               // key rows in flight per MAC thread (registers): 4 at 128 registers, 6 with setmaxnreg 104 / 152
 constexpr int CL_THREADS = 512;                 // warps 0-7: FFT groups, warps 8-15: MAC role (point p = tid - 256)
 constexpr int CL_MAC_WARPS = (CL_THREADS - 256) / 32;
 
@@ -78,7 +81,7 @@ __device__ __forceinline__ double digit_of_level(uint64_t x, int lev) {
 }
 
 // NP = own polynomials of this CTA (3 for rank 0, 2 for rank 1)
-template <int NP>
+template <int NP, bool TIMING>
 __device__ __forceinline__ void cl2_body(const PbsArgs &a, ClSmem &sm, const unsigned rank) {
     const int tid = threadIdx.x;
     const unsigned peer = rank ^ 1u;
@@ -89,12 +92,13 @@ __device__ __forceinline__ void cl2_body(const PbsArgs &a, ClSmem &sm, const uns
     const int n = a.lwe_dim;
     constexpr int ROW_ELEMS = (CL_K + 1) * POLY_M;
     // debug timing (a.dbg != nullptr): clock64() deltas per activity of FFT thread 0 / MAC thread 0 of CTA 0, written to dbg[0..12)
-    const bool timing = a.dbg != nullptr && blockIdx.x == 0 && (tid == 0 || tid == 256);
+    const bool timing = TIMING && blockIdx.x == 0 && (tid == 0 || tid == 256);
     long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = timing ? clock64() : 0;
-#define CT(k) do { if (timing) { const long long t_ = clock64(); tacc[k] += t_ - tlast; tlast = t_; } } while (0)
+#define CT(k) do { if (TIMING && timing) { const long long t_ = clock64(); tacc[k] += t_ - tlast; tlast = t_; } } while (0)
 
     if (tid < 256) {
         // ================================ FFT groups ========================================================================
+        if (CL_PF > 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
         const int gid = tid >> 4, lane = tid & 15;
         const bool active = gid < NROWS;
         const int ls = active ? gid / NP : 0, lp = active ? gid % NP : 0;
@@ -170,6 +174,7 @@ __device__ __forceinline__ void cl2_body(const PbsArgs &a, ClSmem &sm, const uns
         // ================================ MAC role ==========================================================================
         // One ciphertext per cluster: every key value is used exactly once per CTA, so the key rows are not staged in shared
         // memory; thread p reads its K+1 values of a row straight from L2 (all clusters walk the key together), CL_PF rows ahead.
+        if (CL_PF > 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
         const int p = tid - 256, mlane = p & 31;
         const unsigned remote_rx = map_to_peer(&sm.rx[0][0][p], peer), remote_bar = map_to_peer(&sm.rxfull, peer);
         // row g = level_slot * NP + local polynomial of step i in the key stream [i][level slot][row][col][p]
@@ -239,6 +244,7 @@ __device__ __forceinline__ void cl2_body(const PbsArgs &a, ClSmem &sm, const uns
 #undef CT
 }
 
+template <bool TIMING>
 __global__ void __launch_bounds__(CL_THREADS, 1) pbs_cl2_kernel(PbsArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ClSmem &sm = *reinterpret_cast<ClSmem *>(smem_raw);
@@ -266,8 +272,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) pbs_cl2_kernel(PbsArgs a) {
     }
     __syncthreads();
     cluster_sync_all();                               // both CTAs are resident and their barriers initialised before any remote access
-    if (rank == 0) cl2_body<3>(a, sm, rank);
-    else cl2_body<2>(a, sm, rank);
+    if (rank == 0) cl2_body<3, TIMING>(a, sm, rank);
+    else cl2_body<2, TIMING>(a, sm, rank);
     __syncthreads();
     cluster_sync_all();                               // no CTA leaves while its peer may still write into its shared memory
     // sample extract of coefficient 0: mask segment r from polynomial r, body from polynomial K
@@ -284,7 +290,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) pbs_cl2_kernel(PbsArgs a) {
 // one cluster of two CTAs per ciphertext: worthwhile for count <= 74 (one wave)
 cudaError_t launch_pbs_cl2(const PbsArgs &a, cudaStream_t s) {
     const size_t smem = sizeof(ClSmem);
-    cudaError_t e = cudaFuncSetAttribute(pbs_cl2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kernel = a.dbg ? pbs_cl2_kernel<true> : pbs_cl2_kernel<false>;   // a.dbg: per-activity cycle counters (TFA_PBS_TIMING)
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * a.count);
@@ -296,5 +303,5 @@ cudaError_t launch_pbs_cl2(const PbsArgs &a, cudaStream_t s) {
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, pbs_cl2_kernel, a);
+    return cudaLaunchKernelEx(&cfg, kernel, a);
 }

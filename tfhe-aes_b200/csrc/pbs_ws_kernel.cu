@@ -131,7 +131,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
     }
 #if WS_TMEM_ST
     if (tid < 32) {   // warp 0: 64 columns = 32 per FFT warp, two FFT warps per lane quarter
+#if WS_DIAG & 256
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(ws_smem_u32(&sm.tmem_base)) : "memory");
+#else
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(ws_smem_u32(&sm.tmem_base)) : "memory");
+#endif
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -349,7 +353,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
                     for (int g = 0; g < G; g++) x[g] = sm.hs[r * G + g][p];
 #pragma unroll
                     for (int c = 0; c <= K; c++) {   // key values are streamed one at a time (register budget)
-#if WS_DIAG & 1      // diagnostic (wrong results): one key load per row instead of K+1
+#if WS_DIAG & 256    // diagnostic (wrong results): key values read from tensor memory (whatever it holds) instead of the shared-memory ring
+                        cd w;
+                        {
+                            uint32_t t0, t1, t2, t3;
+                            const unsigned ta = sm.tmem_base + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + 64u + (unsigned)(r * 40 + (p >> 7) * 20 + c * 4);
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3) : "r"(ta));
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                            w = cmk(__hiloint2double((int)t1, (int)t0), __hiloint2double((int)t3, (int)t2));
+                        }
+#elif WS_DIAG & 1      // diagnostic (wrong results): one key load per row instead of K+1
                         const cd w = sm.ring[r][0][p];
 #else
                         const cd w = sm.ring[r][c][p];
@@ -406,7 +419,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws_kernel(PbsArgs a) {
 #undef WT
     __syncthreads();
 #if WS_TMEM_ST
+#if WS_DIAG & 256
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(sm.tmem_base) : "memory");
+#else
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(sm.tmem_base) : "memory");
+#endif
 #endif
     // sample extract of coefficient 0
     for (int g = 0; g < G; g++) {
