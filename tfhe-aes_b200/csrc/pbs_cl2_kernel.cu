@@ -28,7 +28,7 @@ constexpr int CL_ROWS = CL_MAXP * CL_LEVELS;    // 15 (level, polynomial) pairs 
 #ifndef CL_PF_ROWS
 #define CL_PF_ROWS 5
 #endif
-constexpr int CL_PF = CL_PF_ROWS;               // key rows in flight per MAC thread (registers): 4 at 128 registers, 6 with setmaxnreg 104 / 152
+constexpr int CL_PF = CL_PF_ROWS;               // key rows in flight per MAC thread (registers; setmaxnreg 112 / 144 above 4).  Measured per wave of 32: 4 rows 5.01 ms, 5 rows 4.73 ms, 6 rows 4.96 ms
 constexpr int CL_THREADS = 512;                 // warps 0-7: FFT groups, warps 8-15: MAC role (point p = tid - 256)
 constexpr int CL_MAC_WARPS = (CL_THREADS - 256) / 32;
 
