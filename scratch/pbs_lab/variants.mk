@@ -1,6 +1,12 @@
-VARIANTS := r1 final d1 d256
+VARIANTS := r1 final ws2
 R1 := -DWS_MAC_REUSE=0 -DWS_REVMAP=0 -DWS_TWB_INV=0 -DWS_ROT_LATE=0 -DWS_MAC_REGS3=120 -DWS_TMEM_ST=0
 FLAGS_r1 := $(R1)
 FLAGS_final :=
-FLAGS_d1 := -DWS_DIAG=1
-FLAGS_d256 := -DWS_DIAG=256
+SRC_ws2 := pbs_ws2_kernel.cu
+FLAGS_ws2 := -DPBS_WS2_NS=ns_ws2 -DPBS_WS2_LAUNCH_NAME=launch_ws2
+VARIANTS += ws2t
+SRC_ws2t := pbs_ws2_kernel.cu
+FLAGS_ws2t := -DPBS_WS2_NS=ns_ws2t -DPBS_WS2_LAUNCH_NAME=launch_ws2t -DWS2_TIMING=1
+VARIANTS += ws2free
+SRC_ws2free := pbs_ws2_kernel.cu
+FLAGS_ws2free := -DPBS_WS2_NS=ns_ws2free -DPBS_WS2_LAUNCH_NAME=launch_ws2free -DWS2_DIAG=1
