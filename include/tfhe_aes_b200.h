@@ -77,7 +77,8 @@ int tfa_ctx_synchronize(tfa_ctx *ctx);
 int tfa_ctx_profile(tfa_ctx *ctx, int enable);
 int tfa_ctx_profile_report(tfa_ctx *ctx, double *ms_per_stage /* [10] */, int *launch_groups /* [10] */);
 /* PBS kernel schedule (same arithmetic): 0 = automatic (default), 1 = phase-synchronous kernel,
- * 2 = warp-specialised kernel.  For tests and measurements; unsupported shapes fall back to the automatic choice. */
+ * 2 = warp-specialised kernel, 3 = one ciphertext per two-CTA cluster (small batches), 4 = two ciphertext sets per CTA taking
+ * turns (large batches; PARAM_OPT shape only).  For tests and measurements; unsupported shapes fall back to the automatic choice. */
 int tfa_ctx_set_pbs_schedule(tfa_ctx *ctx, int schedule);
 /* DFMA microbenchmark: measured FP64 pipe peak of the device in TFLOP/s (roofline denominator) */
 int tfa_measure_fp64_peak(tfa_ctx *ctx, double *tflops);   /* max of the two below */

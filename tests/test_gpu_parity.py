@@ -411,6 +411,35 @@ def test_opt_bootstrap_wave_both_schedules(engine_opt, oracle_opt, count):
     assert torus_absdiff(o.phase_big(res[2][sample]), o.phase_big(ref)) < 2 ** 36
 
 
+@pytest.mark.parametrize("count,schedule", [(7, 4), (900, 0), (1500, 0)])
+def test_opt_bootstrap_two_sets_per_cta(engine_opt, oracle_opt, count, schedule):
+    """pbs_ws2_kernel (two sets of three ciphertexts per CTA, accumulators in tensor memory): same arithmetic as the
+    warp-specialised kernel, so the outputs are bit-identical.  7 forced: ragged last CTA; 900 automatic: one wave of 888 + 12 through
+    the cluster kernel; 1500 automatic: 888 + a remainder above two thirds of a wave, all through pbs_ws2_kernel."""
+    o = oracle_opt
+    rng = np.random.default_rng(count)
+    base = 60
+    msgs0 = rng.integers(0, 2, base).astype(np.uint64)
+    ks0 = o.keyswitch(o.encrypt_bits(msgs0))
+    ks0[:, -1] += np.uint64(1 << 62)
+    pick = rng.integers(0, base, count)
+    ks, msgs = ks0[pick], msgs0[pick]
+    lut = np.full(512, (1 << 64) - (1 << 48), dtype=np.uint64)
+    res = {}
+    for sched in (2, schedule):
+        engine_opt.set_pbs_schedule(sched)
+        try:
+            res[sched] = engine_opt.bootstrap(ks, lut)
+        finally:
+            engine_opt.set_pbs_schedule(0)
+    ph = o.phase_big(res[schedule]) + np.uint64(1 << 48)
+    assert np.array_equal(((ph + np.uint64(1 << 48)) >> np.uint64(49)) & np.uint64(1), msgs)
+    n2 = 888 if count == 900 else count      # ciphertexts that went through pbs_ws2_kernel
+    assert np.array_equal(res[2][:n2], res[schedule][:n2])
+    if n2 < count:                            # the cluster kernel adds the two halves of a row in a different order
+        assert torus_absdiff(o.phase_big(res[2][n2:]), o.phase_big(res[schedule][n2:])) < 2 ** 36
+
+
 def test_opt_many_sbox_noise_within_tolerance(pkg, engine_opt, oracle_opt):
     """north_star: ciphertext noise variance within a stated tolerance of the reference path's.
     Tolerance: variance ratio GPU / oracle in [0.5, 2] over >= 1000 output LWEs."""

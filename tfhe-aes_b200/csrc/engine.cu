@@ -78,6 +78,8 @@ extern "C" int tfa_ctx_create(const tfa_params *p, int device, void *stream, tfa
     ctx->n = p->lwe_dim; ctx->k = p->glwe_dim; ctx->N = p->poly_size;
     ctx->big = ctx->k * ctx->N; ctx->lw = ctx->big + 1; ctx->gsz = (ctx->k + 1) * ctx->N;
     ctx->device = device;
+    ctx->sm_count = 148;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     ctx->launches = 0;
     ctx->profiling = false;
     ctx->pbs_schedule = 0;
@@ -120,7 +122,8 @@ extern "C" void tfa_ctx_destroy(tfa_ctx *ctx) {
 extern "C" const char *tfa_last_error(const tfa_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 extern "C" int tfa_ctx_synchronize(tfa_ctx *ctx) { CU(cudaStreamSynchronize(ctx->stream)); return TFA_OK; }
 extern "C" int tfa_ctx_set_pbs_schedule(tfa_ctx *ctx, int schedule) {
-    if (schedule < 0 || schedule > 3) return ctx->fail(TFA_ERR_PARAM, "pbs schedule must be 0 (auto), 1 (phase-synchronous), 2 (warp-specialised) or 3 (one PBS per two-CTA cluster)");
+    if (schedule < 0 || schedule > 4)
+        return ctx->fail(TFA_ERR_PARAM, "pbs schedule must be 0 (auto), 1 (phase-synchronous), 2 (warp-specialised), 3 (one PBS per two-CTA cluster) or 4 (two sets per CTA)");
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->pbs_schedule = schedule;
     return TFA_OK;
@@ -307,6 +310,27 @@ int dev_pbs(tfa_ctx *ctx, const u64 *in, int count, const u64 *lut, u64 in_scale
     //   phase-synchronous (fp_kernels.cu):   13.1 ms at G = 3
     // The warp-specialised kernel is the default wherever it is instantiated; the phase-synchronous one serves the
     // remaining shapes (K = 1 test parameter sets with G > 1) and stays selectable for comparison.
+    static const bool timing = getenv("TFA_PBS_TIMING") != nullptr;
+    // Large batches: two sets of three ciphertexts per CTA taking turns (pbs_ws2_kernel.cu): 19.2 ms per wave of 888 against
+    // 2 x 10.1 ms.  Whole waves go to it; a remainder of more than two thirds of a wave too (a fourth G = 3 wave plus a partial one
+    // would take as long); a smaller remainder is served by the kernels below, which finish a partial wave sooner.
+    static const bool no_ws2 = getenv("TFA_PBS_NO_WS2") != nullptr;
+    if (ctx->k == 4 && ctx->p.pbs_base_log == 8 && ctx->p.pbs_level == 5 && !timing &&
+        ((ctx->pbs_schedule == 0 && !no_ws2) || ctx->pbs_schedule == 4)) {
+        const int wave = 6 * ctx->sm_count;
+        int n2 = ctx->pbs_schedule == 4 ? count : (count / wave) * wave;
+        if (count - n2 > (2 * wave) / 3) n2 = count;
+        if (n2 > 0) {
+            PbsArgs b = a;
+            b.count = n2;
+            CU(launch_pbs_ws2(ctx->k, 3, ctx->p.pbs_base_log, ctx->p.pbs_level, b, ctx->stream));
+            ctx->launches++;
+            if (n2 == count) return TFA_OK;
+            a.lwe_in += (size_t)n2 * (ctx->n + 1);
+            a.out += (size_t)n2 * (ctx->k * ctx->N + 1);
+            a.count = count -= n2;
+        }
+    }
     // Small batches (at most one wave of two-CTA clusters, 74 ciphertexts): one PBS per cluster, levels transformed in parallel
     // (pbs_cl2_kernel.cu) -- key expansion stages, carry chain of few blocks, a single CTR block.
     static const bool no_cluster = getenv("TFA_PBS_NO_CLUSTER") != nullptr;
@@ -333,7 +357,6 @@ int dev_pbs(tfa_ctx *ctx, const u64 *in, int count, const u64 *lut, u64 in_scale
         return TFA_OK;
     }
     const int G = pick_G(ctx->k, count);
-    static const bool timing = getenv("TFA_PBS_TIMING") != nullptr;
     const bool ws_available = true;   // every (K, G) pick_G returns is instantiated in both kernels
     const bool use_ws = ws_available && ctx->pbs_schedule != 1;
     if (timing && G == 3 && ctx->k == 4) {

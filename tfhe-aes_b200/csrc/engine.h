@@ -13,7 +13,7 @@ typedef uint64_t u64;
 struct tfa_ctx {
     tfa_params p;
     int n, k, N, big, lw, gsz;  // lw = k*N+1 words per big LWE, gsz = (k+1)*N words per GLWE
-    int device;
+    int device, sm_count;
     cudaStream_t stream;
     bool own_stream;
     std::string err;
@@ -42,7 +42,7 @@ struct tfa_ctx {
 
     // optional per-stage GPU timing (tfa_ctx_profile): events around every launch group
     bool profiling;
-    int pbs_schedule;      // 0 auto, 1 phase-synchronous, 2 warp-specialised, 3 cluster pair per ciphertext (tfa_ctx_set_pbs_schedule)
+    int pbs_schedule;      // 0 auto, 1 phase-synchronous, 2 warp-specialised, 3 cluster pair per ciphertext, 4 two sets per CTA (tfa_ctx_set_pbs_schedule)
     struct ProfRec { int stage; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
 

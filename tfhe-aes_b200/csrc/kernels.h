@@ -79,6 +79,7 @@ cudaError_t launch_tc5_keyswitch(const int8_t *dl, int rows_pad, const uint64_t 
 
 cudaError_t launch_pbs(int K, int G, int base_log, int levels, const PbsArgs &a, cudaStream_t s);
 cudaError_t launch_pbs_ws(int K, int G, int base_log, int levels, const PbsArgs &a, cudaStream_t s);
+cudaError_t launch_pbs_ws2(int K, int G, int base_log, int levels, const PbsArgs &a, cudaStream_t s);   // K = 4, G = 3, (2^8, 5): two sets of G per CTA (large batches)
 cudaError_t launch_pbs_cl2(const PbsArgs &a, cudaStream_t s);   // K = 4, (2^8, 5): one ciphertext per cluster of two CTAs (small batches)
 cudaError_t launch_vp(int K, int G, int base_log, int levels, const VpArgs &a, cudaStream_t s);
 cudaError_t launch_cmux_tree(int K, int G, int base_log, int levels, const TreeArgs &a, cudaStream_t s);

@@ -1,21 +1,24 @@
 // pbs_ws2_kernel.cu — warp-specialised PBS with TWO ciphertext sets per CTA taking turns (sm_100a).
 //
 // Same arithmetic and the same two roles as pbs_ws_kernel.cu (FFT warps 8-15, MAC warps 0-7, key rows streamed by TMA into a ring of
-// one level), but the CTA holds NS = 2 sets of G ciphertexts and every role works on the sets alternately, a whole CMux step at a
-// time:
-//     FFT role:  inverse A(i-1), rotate + decompose A(i), forward A(i) levels 5..1, inverse B(i-1), rotate + decompose B(i), ...
-//     MAC role:                                   rows of A(i) levels 5..1, hand over A(i), rows of B(i) ...
+// one level), but the CTA holds NS = 2 sets of G = 3 ciphertexts and each role works on the sets alternately, a CMux step at a time:
+//     MAC role:  rows of A(i) levels 5..1, hand over A(i), rows of B(i) levels 5..1, hand over B(i), rows of A(i+1) ...
+//     FFT role:  while the MAC role is on A(i): forward levels 4..1 of A(i), then inverse transform of B(i-1), rotation +
+//                decomposition of B(i), forward level 5 of B(i); then the same with A and B exchanged.
 // In pbs_ws_kernel the FFT role waits at the end of every step until the MAC role has consumed the last level and handed the
-// Fourier accumulators over, and the MAC role waits while the FFT role runs inverse transform, decomposition and the first forward
-// level (2 400 + 10 200 of 29 000 cycles per step).  Here the other set's work fills both: when the FFT role comes
-// back to set A its hand-over was completed a third of a step ago, so the FFT role, which carries 2/3 of the FP64 work, never waits.
+// Fourier accumulators over (2 900 cycles per step), and the MAC role has nothing to do while the FFT role runs inverse transform,
+// decomposition and the first forward level (10 200).  Here the hand-over of a set is complete long before the FFT role comes back
+// to it, and the MAC role has the last level of the other set to work on during the first 4 800 cycles of that stretch.
 // The key stream delivers the 25 rows of every step twice (once per set): L2 -> SM traffic per ciphertext is unchanged.
+// Measured (scratch/pbs_lab, 888 ciphertexts = one wave, bit-identical outputs): 19.18 ms against 2 x 10.13 ms.
 //
 // What makes the second set fit: the accumulators (G x 20 KB per set) live in TENSOR MEMORY, not in shared memory.  Each FFT lane
 // owns the same 32 coefficients of its polynomial for the whole bootstrap (TMEM is lane-private: 64 columns per set and thread, next
-// to the 32 columns of parked digits), adds the rounded inverse transform to them there (tcgen05.ld / tcgen05.st), and drops a copy
-// into its own hand-over slot, which is idle between the inverse transform and the first forward level; the rotation X^a gathers
-// from that copy.  Shared memory: 2 x 60 KB slots + 100 KB key ring + 4 KB twiddles.
+// to 40 columns of parked digits per set), adds the rounded inverse transform to them there (tcgen05.ld / tcgen05.st), and drops a
+// copy into its own hand-over slot, which is idle between the inverse transform and the first forward level; the rotation X^a
+// gathers from that copy.  Shared memory: 2 x 60 KB slots + 100 KB key ring + 4 KB twiddles; tensor memory: all 512 columns.
+// The FFT role is a table-driven loop over three self-contained activities (forward level, end of step, start of step): no
+// register state crosses from one to the next, every digit level comes back from tensor memory, and the order is a macro.
 #include "ws_common.cuh"
 
 #ifndef PBS_WS2_NS
@@ -25,10 +28,12 @@
 #define PBS_WS2_LAUNCH_NAME launch_pbs_ws2
 #endif
 #ifndef WS2_MAC_REGS
-#define WS2_MAC_REGS 112
+#define WS2_MAC_REGS 120
 #endif
-#ifndef WS2_DIAG
-#define WS2_DIAG 0        // scratch/pbs_lab diagnostics (results WRONG): 1 = the roles never wait for each other's spectra / slots / hand-over
+#ifndef WS2_ORDER
+#define WS2_ORDER 0x5761234   // program of the FFT role per half-period, first activity in the low nibble (see the loop in the kernel):
+                              // levels 4..1 of X, then end of step / start of step / level 5 of Y.  Measured per 888 ciphertexts: this order
+                              // 19.18 ms; Y's work slotted between X's levels (0x1527364, 0x5712364, 0x5716234, 0x5176234) 19.4-20.7 ms
 #endif
 #ifndef WS2_TIMING
 #define WS2_TIMING 0      // scratch/pbs_lab: per-activity clock64() sums of CTA 0 (FFT thread 0, MAC thread 0) into PbsArgs::dbg[0..9)
@@ -75,9 +80,9 @@ __device__ __forceinline__ void cmac_cols2(cd (&facc)[G][KP1], int c, const cd (
     for (int g = 0; g < G; g++) facc[g][c].y = fma(x[g].y, w.x, facc[g][c].y);
 }
 
-// TMEM columns per FFT thread (two FFT warps share a lane quarter, 256 columns each): [0, 32) parked digits, [32 + 64 s, 96 + 64 s)
-// the 32 accumulator coefficients of set s: coefficient 16 n1 + lane at columns 4 n1 (lo), 4 n1 + 1 (hi), + 256 at 4 n1 + 2, 4 n1 + 3
-constexpr int TM_DIGITS = 0, TM_ACC = 32, TM_PER_WARP = 256;
+// TMEM columns per FFT thread (two FFT warps share a lane quarter, 256 columns each): [64 s, 64 s + 40) the parked digits of set s
+// (levels 4..1 at 8 (4 - lev), level 5 at 32), [128 + 64 s, 192 + 64 s) the 32 accumulator coefficients of set s: coefficient 16 n1 + lane at columns 4 n1 (lo), 4 n1 + 1 (hi), + 256 at 4 n1 + 2, 4 n1 + 3
+constexpr int TM_DIGITS = 0, TM_ACC = 128, TM_PER_WARP = 256;
 
 template <int K, int G, int NS, int BASE_LOG, int LEVELS>
 __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws2_kernel(PbsArgs a) {
@@ -132,8 +137,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws2_kernel(PbsArgs a) {
         const int r_a = gid_a / G;
         const int r_b = (gid_b < G * (K + 1)) ? gid_b / G : r_a;
         (void)r_a;
-        cd v[16];
-        uint32_t st_re[16], st_im[16];
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const unsigned taddr = sm.tmem_base + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)((ftid >> 7) * TM_PER_WARP);
         if (gid_a < G * (K + 1)) {
@@ -160,91 +163,137 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws2_kernel(PbsArgs a) {
             }
             ws_tmem_wait_st();
             __syncwarp();
-#pragma unroll 1
-            for (int i = 0; i <= n; i++) {
-#pragma unroll 1
-                for (int s = 0; s < NS; s++) {
-                    cd *slot = sm.hs[s][active ? gid : 0];
-                    const int my_ct = min(ct0 + s * G + ct, a.count - 1);
-                    // raw mask element of step i: fetched before the inverse transform, mod-switched after it
-                    const uint64_t raw = a.lwe_in[(size_t)my_ct * (n + 1) + min(i, n - 1)];
-                    if (i > 0) {
-                        // ---- finish step i-1: inverse transform of the Fourier accumulator the MAC warps left in this group's slot
-                        WT(3);
-                        if (!(WS2_DIAG & 1)) ws_mbar_wait(&sm.inv[s], (i - 1) & 1);
-                        WT(4);
+
+            // ---- the three activities of the FFT role; each is self-contained (no register state crosses from one to the next)
+            // forward transform of level lev of set s, step i: digits from tensor memory -> spectrum in the slot
+            auto slot_of = [&](int s) {
+                int off = s * (K + 1) * G * XB_ELEMS;
+                asm volatile("" : "+r"(off));     // opaque: keeps per-set addresses from being precomputed (and spilled) outside the loop
+                return &sm.hs[0][active ? gid : 0][0] + off;
+            };
+            auto forward_level = [&](int s, int lev, int i) {
+                cd *slot = slot_of(s);
+                cd v[16];
+                {
+                    uint32_t pk[8];
+                    ws_tmem_ld8(taddr + TM_DIGITS + 64 * s + (lev == LEVELS ? 4 : 4 - lev) * 8, pk);
 #pragma unroll
-                        for (int k2 = 0; k2 < 16; k2++) v[k2] = slot[lane + 16 * k2];
-                        fft256_inv_pass1_compute(v);
-                        __syncwarp();
-                        if (active) fft256_inv_pass1_store_b<8>(v, lane, sm.tw, slot);
-                        __syncwarp();
-                        fft256_inv_pass2(v, lane, slot);
-                        __syncwarp();       // every lane has read the slot: it now takes the accumulator copy
-                        uint64_t *copy = reinterpret_cast<uint64_t *>(slot);
+                    for (int n1 = 0; n1 < 16; n1++) v[n1] = cmk(digit85(pk[n1 >> 2], n1 & 3), digit85(pk[4 + (n1 >> 2)], n1 & 3));
+                }
+                fft256_fwd_pass1_compute(v, lane, sm.tw);
+                WT(1);
+                // the MAC warps have consumed the previous occupant of the slot (they release the rows of a level in order)
+                const unsigned produced = (unsigned)(i * LEVELS + (LEVELS - lev));   // levels of this set produced so far
+                if (produced > 0) ws_mbar_wait(&sm.rempty[s][r_b], (produced - 1) & 1);
+                WT(2);
+                if (active) fft256_fwd_pass1_store(v, lane, slot);
+                __syncwarp();
+                fft256_fwd_pass2(v, lane, slot);
+                __syncwarp();
+                if (active) {
 #pragma unroll
-                        for (int c = 0; c < 4; c++) {
-                            uint32_t w[16];
-                            tmem_ld16(taddr + TM_ACC + 64 * s + 16 * c, w);
+                    for (int k2 = 0; k2 < 16; k2++) slot[lane + 16 * k2] = v[rev4(k2)];
+                }
+                __syncwarp();
+                if (active && lane == 0) ws_mbar_arrive(&sm.rfull[s][r & ~1]);
+                WT(3);
+            };
+            // end of step i of set s: inverse transform of the Fourier accumulator the MAC warps left in the slot, added to the
+            // accumulator in tensor memory; the slot keeps a copy for the rotation of the next step
+            auto finish_step = [&](int s, int i) {
+                cd *slot = slot_of(s);
+                cd v[16];
+                ws_mbar_wait(&sm.inv[s], i & 1);
+                WT(4);
 #pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                const int n1 = 4 * c + k, j = 16 * n1 + lane;
-                                const uint64_t a0 = (((uint64_t)w[4 * k + 1] << 32) | w[4 * k]) + f64_to_torus(v[n1].x);
-                                const uint64_t a1 = (((uint64_t)w[4 * k + 3] << 32) | w[4 * k + 2]) + f64_to_torus(v[n1].y);
-                                w[4 * k] = (uint32_t)a0; w[4 * k + 1] = (uint32_t)(a0 >> 32);
-                                w[4 * k + 2] = (uint32_t)a1; w[4 * k + 3] = (uint32_t)(a1 >> 32);
-                                if (active) { copy[j] = a0; copy[j + POLY_M] = a1; }
-                            }
-                            tmem_st16(taddr + TM_ACC + 64 * s + 16 * c, w);
-                        }
-                        ws_tmem_wait_st();
-                        __syncwarp();
-                        WT(5);
+                for (int k2 = 0; k2 < 16; k2++) v[k2] = slot[lane + 16 * k2];
+                fft256_inv_pass1_compute(v);
+                __syncwarp();
+                if (active) fft256_inv_pass1_store_b<8>(v, lane, sm.tw, slot);
+                __syncwarp();
+                fft256_inv_pass2(v, lane, slot);
+                __syncwarp();       // every lane has read the slot: it now takes the accumulator copy
+                uint64_t *copy = reinterpret_cast<uint64_t *>(slot);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t w[16];
+                    tmem_ld16(taddr + TM_ACC + 64 * s + 16 * c, w);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int n1 = 4 * c + k, j = 16 * n1 + lane;
+                        const uint64_t a0 = (((uint64_t)w[4 * k + 1] << 32) | w[4 * k]) + f64_to_torus(v[n1].x);
+                        const uint64_t a1 = (((uint64_t)w[4 * k + 3] << 32) | w[4 * k + 2]) + f64_to_torus(v[n1].y);
+                        w[4 * k] = (uint32_t)a0; w[4 * k + 1] = (uint32_t)(a0 >> 32);
+                        w[4 * k + 2] = (uint32_t)a1; w[4 * k + 3] = (uint32_t)(a1 >> 32);
+                        if (active) { copy[j] = a0; copy[j + POLY_M] = a1; }
                     }
-                    if (i < n) {
-                        // ---- start step i: rotate-subtract from the copy, decompose, park the digits of levels 4..1
-                        const int rot = (int)((raw * a.in_scale + (1ull << 53)) >> 54) & (2 * POLY_N - 1);
-                        load_decompose_rot<BASE_LOG, LEVELS>(reinterpret_cast<const uint64_t *>(slot), lane, rot, v, st_re, st_im);
+                    tmem_st16(taddr + TM_ACC + 64 * s + 16 * c, w);
+                }
+                ws_tmem_wait_st();
+                __syncwarp();
+                WT(5);
+            };
+            // start of step i of set s: (acc * X^a - acc) gathered from the copy, signed decomposition, all five digit levels parked
+            // in tensor memory (one word per four coefficients and level)
+            auto start_step = [&](int s, uint64_t raw) {
+                const uint64_t *poly = reinterpret_cast<const uint64_t *>(slot_of(s));
+                asm volatile("" : "+l"(raw)::"memory");   // the rotation arithmetic stays here (it was being hoisted to the fetch and spilled)
+                const int rot = (int)((raw * a.in_scale + (1ull << 53)) >> 54) & (2 * POLY_N - 1);
+                const int s0 = (lane - rot) & (2 * POLY_N - 1);
+                uint32_t st_re[16], st_im[16], p5[8];
 #pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            uint32_t pk[8];
+                for (int q4 = 0; q4 < 4; q4++) {
+                    uint32_t lo_re[4], lo_im[4];
 #pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                pk[j] = ws_gather_byte(st_re[4 * j], st_re[4 * j + 1], st_re[4 * j + 2], st_re[4 * j + 3], b);
-                                pk[4 + j] = ws_gather_byte(st_im[4 * j], st_im[4 * j + 1], st_im[4 * j + 2], st_im[4 * j + 3], b);
-                            }
-                            ws_tmem_st8(taddr + TM_DIGITS + b * 8, pk);
-                        }
-                        ws_tmem_wait_st();
-                        __syncwarp();       // the copy has been gathered by every lane before the first spectrum overwrites it
-                        WT(0);
-#pragma unroll 1
-                        for (int lev = LEVELS; lev >= 1; lev--) {
-                            const unsigned produced = (unsigned)(i * LEVELS + (LEVELS - lev));   // levels of this set produced so far
-                            if (lev != LEVELS) {
-                                uint32_t pk[8];
-                                ws_tmem_ld8(taddr + TM_DIGITS + (4 - lev) * 8, pk);
-#pragma unroll
-                                for (int n1 = 0; n1 < 16; n1++) v[n1] = cmk(digit85(pk[n1 >> 2], n1 & 3), digit85(pk[4 + (n1 >> 2)], n1 & 3));
-                            }
-                            fft256_fwd_pass1_compute(v, lane, sm.tw);
-                            WT(1);
-                            // the MAC warps have consumed the previous occupant of the slot (they release the rows of a level in order)
-                            if (produced > 0 && !(WS2_DIAG & 1)) ws_mbar_wait(&sm.rempty[s][r_b], (produced - 1) & 1);
-                            WT(2);
-                            if (active) fft256_fwd_pass1_store(v, lane, slot);
-                            __syncwarp();
-                            fft256_fwd_pass2(v, lane, slot);
-                            __syncwarp();
-                            if (active) {
-#pragma unroll
-                                for (int k2 = 0; k2 < 16; k2++) slot[lane + 16 * k2] = v[rev4(k2)];
-                            }
-                            __syncwarp();
-                            if (active && lane == 0) ws_mbar_arrive(&sm.rfull[s][r & ~1]);
-                            WT(3);
-                        }
+                    for (int k = 0; k < 4; k++) {
+                        const int n1 = 4 * q4 + k, j = 16 * n1 + lane;
+                        const int sh = (s0 + 16 * n1) & (2 * POLY_N - 1);
+                        const int i0 = sh & (POLY_N - 1);
+                        const uint64_t x0 = poly[i0], x1 = poly[i0 ^ POLY_M];
+                        const uint64_t m0 = (uint64_t)0 - (uint64_t)((sh >> 9) & 1);
+                        const uint64_t m1 = (uint64_t)0 - (uint64_t)(((sh >> 9) ^ (sh >> 8)) & 1);
+                        const uint64_t y0 = ((x0 ^ m0) - m0) - poly[j] + DECOMP85_ADD;            // decomp85_first
+                        const uint64_t y1 = ((x1 ^ m1) - m1) - poly[j + POLY_M] + DECOMP85_ADD;
+                        lo_re[k] = (uint32_t)y0; st_re[n1] = (uint32_t)(y0 >> 32);
+                        lo_im[k] = (uint32_t)y1; st_im[n1] = (uint32_t)(y1 >> 32);
                     }
+                    p5[q4] = ws_gather_byte(lo_re[0], lo_re[1], lo_re[2], lo_re[3], 3);
+                    p5[4 + q4] = ws_gather_byte(lo_im[0], lo_im[1], lo_im[2], lo_im[3], 3);
+                }
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        pk[j] = ws_gather_byte(st_re[4 * j], st_re[4 * j + 1], st_re[4 * j + 2], st_re[4 * j + 3], b);
+                        pk[4 + j] = ws_gather_byte(st_im[4 * j], st_im[4 * j + 1], st_im[4 * j + 2], st_im[4 * j + 3], b);
+                    }
+                    ws_tmem_st8(taddr + TM_DIGITS + 64 * s + b * 8, pk);
+                }
+                ws_tmem_st8(taddr + TM_DIGITS + 64 * s + 32, p5);
+                ws_tmem_wait_st();
+                __syncwarp();       // the copy has been gathered by every lane before the first spectrum overwrites it
+                WT(0);
+            };
+
+            // Program of one half-period h (the MAC role consumes step i of set X = h & 1 meanwhile; Y is the other set): the forward
+            // levels 4..1 of X, each due when the MAC role has consumed the level before it, with the end of Y's previous step, the
+            // start of its next one and its first level slotted in between.  h = -1 and h = 2n are the ramps (only Y's part runs).
+#pragma unroll 1
+            for (int h = -1; h <= 2 * n; h++) {
+                const int X = h & 1, Y = X ^ 1, i = h >> 1;
+                const bool xlive = h >= 0 && h < 2 * n;
+                const int y_fin = X == 0 ? i - 1 : i, y_new = y_fin + 1;
+                // mask element of Y's next step: fetched a whole half-period's worth of work before it is used
+                const uint64_t raw = a.lwe_in[(size_t)min(ct0 + Y * G + ct, a.count - 1) * (n + 1) + min(y_new, n - 1)];
+#pragma unroll 1
+                for (int op = 0; op < 7; op++) {
+                    const int code = (WS2_ORDER >> (4 * op)) & 15;     // 1-4: forward level of X, 5: forward level 5 of Y, 6: finish Y, 7: start Y
+                    if (code <= 5) {
+                        const bool isx = code <= 4;
+                        if (isx ? xlive : y_new < n) forward_level(isx ? X : Y, isx ? code : LEVELS, isx ? i : y_new);
+                    } else if (code == 6) { if (y_fin >= 0) finish_step(Y, y_fin); }
+                    else { if (y_new < n) start_step(Y, raw); }
                 }
             }
             if (WS2_TIMING && a.dbg && blockIdx.x == 0 && ftid == 0)
@@ -281,10 +330,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws2_kernel(PbsArgs a) {
                     const unsigned pr = (unsigned)(i * LEVELS + (LEVELS - lev)) & 1;      // spectra of this set
 #pragma unroll
                     for (int r = 0; r <= K; r++, q++) {
-                        if (WS2_DIAG & 1) {
-                            if (r == 0) ws_mbar_wait(&sm.bfull[0], parity);
-                            else if (r == BSPLIT) ws_mbar_wait(&sm.bfull[1], parity);
-                        } else if (r == 0) ws_mbar_wait2(&sm.bfull[0], parity, &sm.rfull[s][0], pr);
+                        if (r == 0) ws_mbar_wait2(&sm.bfull[0], parity, &sm.rfull[s][0], pr);
                         else if (r == BSPLIT && (r & 1) == 0) ws_mbar_wait2(&sm.bfull[1], parity, &sm.rfull[s][r], pr);
                         else if (r == BSPLIT) ws_mbar_wait(&sm.bfull[1], parity);
                         else if ((r & 1) == 0) ws_mbar_wait(&sm.rfull[s][r], pr);
