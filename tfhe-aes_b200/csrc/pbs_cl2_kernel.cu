@@ -10,10 +10,10 @@
 //     re-derives the rotated difference and keeps only its own digit: no digit state, no hand-over between groups);
 //   * each CTA multiplies only the key rows of its own polynomials (15 / 10 of the 25 rows) into partial Fourier accumulators of
 //     all K+1 output columns; with one ciphertext every key value is used once per CTA, so the rows are not staged in shared
-//     memory: each MAC thread reads its five values of a row straight from L2, four rows ahead in registers;
-//   * the partial sums of the columns the other CTA owns go to its shared memory (st.shared::cluster, 8 / 12 KB per step) followed
-//     by one arrival per warp on the peer's mbarrier (release / acquire at cluster scope), and the owner adds the two halves,
-//     inverse-transforms and updates its polynomials.
+//     memory: each MAC thread reads its five values of a row straight from L2, CL_PF = 5 rows ahead in registers;
+//   * the partial sums of the columns the other CTA owns go to its shared memory with st.async (8 / 12 KB per step, byte-counted on
+//     the receiver's mbarrier: no release fence, no arrival, the sender does not wait for the round trip), and the owner adds the
+//     two halves, inverse-transforms and updates its polynomials.
 // Arithmetic, decomposition (tie rule included) and FFT are those of pbs_ws_kernel (cmux_core.cuh / fft_core.cuh); only the order
 // in which the 25 products are summed differs (per CTA, then across), i.e. the last bits of the floating-point sums.
 #include <cuda.h>
