@@ -35,6 +35,12 @@
                               // levels 4..1 of X, then end of step / start of step / level 5 of Y.  Measured per 888 ciphertexts: this order
                               // 19.18 ms; Y's work slotted between X's levels (0x1527364, 0x5712364, 0x5716234, 0x5176234) 19.4-20.7 ms
 #endif
+#ifndef WS2_EARLY_RELEASE
+#define WS2_EARLY_RELEASE 0   // 1: spectra and key slot released right after the first FMA pass (all loads have returned by then): 19.26 ms
+#endif                        //    against 18.94 (the barrier traffic in the middle of the FMA block costs more than the earlier refill gains)
+#ifndef WS2_MAC_WIDE
+#define WS2_MAC_WIDE 1     // all K+1 key values of a row first, then four FMA passes over all (g, c): dependent FMAs 15 apart (19.17 -> 18.92 ms per 888)
+#endif
 #ifndef WS2_TIMING
 #define WS2_TIMING 0      // scratch/pbs_lab: per-activity clock64() sums of CTA 0 (FFT thread 0, MAC thread 0) into PbsArgs::dbg[0..9)
 #endif
@@ -335,25 +341,59 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws2_kernel(PbsArgs a) {
                         else if (r == BSPLIT) ws_mbar_wait(&sm.bfull[1], parity);
                         else if ((r & 1) == 0) ws_mbar_wait(&sm.rfull[s][r], pr);
                         WT(0);
+                        auto release_row = [&]() {
+                            __syncwarp();
+                            if (mlane == 0) {
+                                ws_mbar_arrive(&sm.bempty[r]);
+                                if (lev > 1) ws_mbar_arrive(&sm.rempty[s][r]);   // after the last level the slot is released below
+                                if (mwarp == (q & (WS_MAC_WARPS - 1)) && q >= 1 && q - 1 + RING < nrows) {
+                                    const int ps = (r + K) % RING;                              // slot of row q - 1
+                                    const unsigned pp = (r == 0) ? (parity ^ 1) : parity;       // its level
+                                    ws_mbar_wait(&sm.bempty[ps], pp);
+                                    produce(q - 1 + RING);
+                                }
+                            }
+                        };
                         cd x[G];
 #pragma unroll
                         for (int g = 0; g < G; g++) x[g] = sm.hs[s][r * G + g][p];
+#if WS2_MAC_WIDE
+                        {   // all K+1 key values first, then the four FMA passes over all (g, c): dependent FMAs are 15 apart
+                            cd w[K + 1];
+#pragma unroll
+                            for (int c = 0; c <= K; c++) w[c] = sm.ring[r][c][p];
+#pragma unroll
+                            for (int c = 0; c <= K; c++)
+#pragma unroll
+                                for (int g = 0; g < G; g++) facc[g][c].x = fma(x[g].x, w[c].x, facc[g][c].x);
+#if WS2_EARLY_RELEASE
+                            // every 16-byte load of the row has fed an FMA above (in-order issue: they have all returned): the spectra
+                            // slot and the key slot can go back to their producers three FMA passes before this warp is done with the row
+                            release_row();
+#endif
+#pragma unroll
+                            for (int c = 0; c <= K; c++)
+#pragma unroll
+                                for (int g = 0; g < G; g++) facc[g][c].y = fma(x[g].x, w[c].y, facc[g][c].y);
+#pragma unroll
+                            for (int c = 0; c <= K; c++)
+#pragma unroll
+                                for (int g = 0; g < G; g++) facc[g][c].x = fma(-x[g].y, w[c].y, facc[g][c].x);
+#pragma unroll
+                            for (int c = 0; c <= K; c++)
+#pragma unroll
+                                for (int g = 0; g < G; g++) facc[g][c].y = fma(x[g].y, w[c].x, facc[g][c].y);
+                        }
+#else
 #pragma unroll
                         for (int c = 0; c <= K; c++) {
                             const cd w = sm.ring[r][c][p];
                             cmac_cols2<G, K + 1>(facc, c, x, w);
                         }
-                        __syncwarp();
-                        if (mlane == 0) {
-                            ws_mbar_arrive(&sm.bempty[r]);
-                            if (lev > 1) ws_mbar_arrive(&sm.rempty[s][r]);   // after the last level the slot is released below
-                            if (mwarp == (q & (WS_MAC_WARPS - 1)) && q >= 1 && q - 1 + RING < nrows) {
-                                const int ps = (r + K) % RING;                              // slot of row q - 1
-                                const unsigned pp = (r == 0) ? (parity ^ 1) : parity;       // its level
-                                ws_mbar_wait(&sm.bempty[ps], pp);
-                                produce(q - 1 + RING);
-                            }
-                        }
+#endif
+#if !(WS2_MAC_WIDE && WS2_EARLY_RELEASE)
+                        release_row();
+#endif
                         WT(1);
                     }
                     level_count++;
