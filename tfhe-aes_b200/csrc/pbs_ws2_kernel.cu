@@ -38,6 +38,9 @@
 #ifndef WS2_EARLY_RELEASE
 #define WS2_EARLY_RELEASE 0   // 1: spectra and key slot released right after the first FMA pass (all loads have returned by then): 19.26 ms
 #endif                        //    against 18.94 (the barrier traffic in the middle of the FMA block costs more than the earlier refill gains)
+#ifndef WS2_NAMED_BAR
+#define WS2_NAMED_BAR 0
+#endif
 #ifndef WS2_MAC_WIDE
 #define WS2_MAC_WIDE 1     // all K+1 key values of a row first, then four FMA passes over all (g, c): dependent FMAs 15 apart (19.17 -> 18.92 ms per 888)
 #endif
@@ -73,6 +76,9 @@ __device__ __forceinline__ void tmem_st16(unsigned taddr, const uint32_t (&r)[16
                  "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
                  : "memory");
 }
+
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 template <int G, int KP1>
 __device__ __forceinline__ void cmac_cols2(cd (&facc)[G][KP1], int c, const cd (&x)[G], cd w) {
@@ -201,7 +207,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws2_kernel(PbsArgs a) {
                     for (int k2 = 0; k2 < 16; k2++) slot[lane + 16 * k2] = v[rev4(k2)];
                 }
                 __syncwarp();
+#if WS2_NAMED_BAR
+                // hardware barrier 1 + 3 s + pair: the FFT warps of the pair arrive, the eight MAC warps wait in bar.sync (asleep, no polling)
+                named_arrive(1 + 3 * s + (r_a >> 1), WS_THREADS - WS_FFT_THREADS + 32 * ((r_a >> 1) == 2 ? 2 : 3));
+#else
                 if (active && lane == 0) ws_mbar_arrive(&sm.rfull[s][r & ~1]);
+#endif
                 WT(3);
             };
             // end of step i of set s: inverse transform of the Fourier accumulator the MAC warps left in the slot, added to the
@@ -336,10 +347,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws2_kernel(PbsArgs a) {
                     const unsigned pr = (unsigned)(i * LEVELS + (LEVELS - lev)) & 1;      // spectra of this set
 #pragma unroll
                     for (int r = 0; r <= K; r++, q++) {
+#if WS2_NAMED_BAR
+                        if ((r & 1) == 0) named_sync(1 + 3 * s + (r >> 1), WS_THREADS - WS_FFT_THREADS + 32 * ((r >> 1) == 2 ? 2 : 3));
+                        if (r == 0) ws_mbar_wait(&sm.bfull[0], parity);
+                        else if (r == BSPLIT) ws_mbar_wait(&sm.bfull[1], parity);
+#else
                         if (r == 0) ws_mbar_wait2(&sm.bfull[0], parity, &sm.rfull[s][0], pr);
                         else if (r == BSPLIT && (r & 1) == 0) ws_mbar_wait2(&sm.bfull[1], parity, &sm.rfull[s][r], pr);
                         else if (r == BSPLIT) ws_mbar_wait(&sm.bfull[1], parity);
                         else if ((r & 1) == 0) ws_mbar_wait(&sm.rfull[s][r], pr);
+#endif
                         WT(0);
                         auto release_row = [&]() {
                             __syncwarp();
