@@ -41,6 +41,9 @@
 #ifndef WS2_NAMED_BAR
 #define WS2_NAMED_BAR 0
 #endif
+#ifndef WS2_RFULL_PER_ROW
+#define WS2_RFULL_PER_ROW 0
+#endif
 #ifndef WS2_MAC_WIDE
 #define WS2_MAC_WIDE 1     // all K+1 key values of a row first, then four FMA passes over all (g, c): dependent FMAs 15 apart (19.17 -> 18.92 ms per 888)
 #endif
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws2_kernel(PbsArgs a) {
     if (tid == 0) {
         for (int s = 0; s < NS; s++) {
             for (int r = 0; r <= K; r++) {
-                ws_mbar_init(&sm.rfull[s][r], G * ((r | 1) <= K ? 2 : 1));   // shared by the row pairs (0,1), (2,3), (4)
+                ws_mbar_init(&sm.rfull[s][r], WS2_RFULL_PER_ROW ? G : G * ((r | 1) <= K ? 2 : 1));   // shared by the row pairs (0,1), (2,3), (4)
                 ws_mbar_init(&sm.rempty[s][r], WS_MAC_WARPS);
             }
             ws_mbar_init(&sm.inv[s], WS_MAC_WARPS);
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws2_kernel(PbsArgs a) {
                 // hardware barrier 1 + 3 s + pair: the FFT warps of the pair arrive, the eight MAC warps wait in bar.sync (asleep, no polling)
                 named_arrive(1 + 3 * s + (r_a >> 1), WS_THREADS - WS_FFT_THREADS + 32 * ((r_a >> 1) == 2 ? 2 : 3));
 #else
-                if (active && lane == 0) ws_mbar_arrive(&sm.rfull[s][r & ~1]);
+                if (active && lane == 0) ws_mbar_arrive(&sm.rfull[s][WS2_RFULL_PER_ROW ? r : (r & ~1)]);
 #endif
                 WT(3);
             };
@@ -351,6 +354,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws2_kernel(PbsArgs a) {
                         if ((r & 1) == 0) named_sync(1 + 3 * s + (r >> 1), WS_THREADS - WS_FFT_THREADS + 32 * ((r >> 1) == 2 ? 2 : 3));
                         if (r == 0) ws_mbar_wait(&sm.bfull[0], parity);
                         else if (r == BSPLIT) ws_mbar_wait(&sm.bfull[1], parity);
+#elif WS2_RFULL_PER_ROW
+                        if (r == 0) ws_mbar_wait2(&sm.bfull[0], parity, &sm.rfull[s][0], pr);
+                        else if (r == BSPLIT) ws_mbar_wait2(&sm.bfull[1], parity, &sm.rfull[s][r], pr);
+                        else ws_mbar_wait(&sm.rfull[s][r], pr);
 #else
                         if (r == 0) ws_mbar_wait2(&sm.bfull[0], parity, &sm.rfull[s][0], pr);
                         else if (r == BSPLIT && (r & 1) == 0) ws_mbar_wait2(&sm.bfull[1], parity, &sm.rfull[s][r], pr);
