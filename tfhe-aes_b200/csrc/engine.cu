@@ -311,7 +311,7 @@ int dev_pbs(tfa_ctx *ctx, const u64 *in, int count, const u64 *lut, u64 in_scale
     // The warp-specialised kernel is the default wherever it is instantiated; the phase-synchronous one serves the
     // remaining shapes (K = 1 test parameter sets with G > 1) and stays selectable for comparison.
     static const bool timing = getenv("TFA_PBS_TIMING") != nullptr;
-    // Large batches: two sets of three ciphertexts per CTA taking turns (pbs_ws2_kernel.cu): 19.2 ms per wave of 888 against
+    // Large batches: two sets of three ciphertexts per CTA taking turns (pbs_ws2_kernel.cu): 18.9 ms per wave of 888 against
     // 2 x 10.1 ms.  Whole waves go to it; a remainder of more than five sixths of a wave too (two G = 3 waves would take 20.2 ms); a
     // smaller remainder is served by the kernels below, which finish a partial wave sooner (10.1 + 7.6 ... 8.7 ms up to 740).
     static const bool no_ws2 = getenv("TFA_PBS_NO_WS2") != nullptr;

@@ -10,7 +10,7 @@
 // decomposition and the first forward level (10 200).  Here the hand-over of a set is complete long before the FFT role comes back
 // to it, and the MAC role has the last level of the other set to work on during the first 4 800 cycles of that stretch.
 // The key stream delivers the 25 rows of every step twice (once per set): L2 -> SM traffic per ciphertext is unchanged.
-// Measured (scratch/pbs_lab, 888 ciphertexts = one wave, bit-identical outputs): 19.18 ms against 2 x 10.13 ms.
+// Measured (scratch/pbs_lab, 888 ciphertexts = one wave, bit-identical outputs): 18.92 ms against 2 x 10.13 ms.
 //
 // What makes the second set fit: the accumulators (G x 20 KB per set) live in TENSOR MEMORY, not in shared memory.  Each FFT lane
 // owns the same 32 coefficients of its polynomial for the whole bootstrap (TMEM is lane-private: 64 columns per set and thread, next
