@@ -36,7 +36,7 @@ def pbs_per_block(blocks):       # batched tfa_aes_ctr: IV bits bootstrapped onc
 
 
 BSK_BYTES = 342_528_000
-NCU_DRAM_BYTES_PER_WAVE = 352_896_768   # ncu --set full, pbs_ws2_kernel<4,3,2,8,5>, 148 CTAs x 6 ciphertexts (profiles/r2_pbs_ws2_kernel_ncu.txt: 348.61 MB read + 4.28 MB written)
+NCU_DRAM_BYTES_PER_WAVE = 354_475_264   # ncu --set full, pbs_ws2_kernel<4,3,2,8,5>, 148 CTAs x 6 ciphertexts (profiles/r2_pbs_ws2_kernel_ncu.txt: 348.85 MB read + 5.62 MB written)
 PBS_WAVE = 6 * 148                      # ciphertexts per wave of the dominant kernel
 METRIC = "aes128_ctr_blocks_per_s"
 UNIT = "blocks/s"
@@ -431,7 +431,7 @@ def run_gpu(args):
             "roofline": {"bound": "fp64", "kernel": "pbs_ws2_kernel<4,3,2,8,5>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
                          "peak_source": "max of the DFMA and the mma.sync.m8n8k4.f64 microbenchmarks of the FP64 pipe in this run (MEASURED_PEAKS.json has no FP64 figure)",
                          "peak_dfma": peak_dfma, "peak_dmma": peak_dmma, "traffic": NCU_DRAM_BYTES_PER_WAVE * -(-count // PBS_WAVE),
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one 888-PBS wave (profiles/r2_pbs_ws2_kernel_ncu.txt: 348.6 + 4.3 MB) x waves in this launch (the last 296 of 18 944 run as a wave of pbs_ws_kernel<4,2,8,5>); algorithmic = 342.5 MB of key per wave",
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one 888-PBS wave (profiles/r2_pbs_ws2_kernel_ncu.txt: 348.9 + 5.6 MB) x waves in this launch (the last 296 of 18 944 run as a wave of pbs_ws_kernel<4,2,8,5>); algorithmic = 342.5 MB of key per wave",
                          "launch_ms": pbs_ms, "pbs_per_launch": count, "flop_per_pbs": PBS_FLOP,
                          "bsk_hbm_gbs": BSK_BYTES * -(-count // PBS_WAVE) / (pbs_ms * 1e-3) * 1e-9, "hbm_peak_gbs": hbm,
                          "note": "the key (342.5 MB) is read from HBM once per wave of 888 PBS and served from L2 to the other CTAs"},
