@@ -27,8 +27,9 @@
 #ifndef PBS_WS2_LAUNCH_NAME
 #define PBS_WS2_LAUNCH_NAME launch_pbs_ws2
 #endif
+// Tuning switches; the defaults are what scratch/pbs_lab measured best on B200 (profiles/r2_pbs_lab_ws2.txt), every variant bit-identical.
 #ifndef WS2_MAC_REGS
-#define WS2_MAC_REGS 120
+#define WS2_MAC_REGS 120      // registers per MAC thread (FFT threads get 256 - this): 112 spills in the MAC role (20.23 ms), 128 in the FFT role (19.04)
 #endif
 #ifndef WS2_ORDER
 #define WS2_ORDER 0x5761234   // program of the FFT role per half-period, first activity in the low nibble (see the loop in the kernel):
@@ -39,10 +40,10 @@
 #define WS2_EARLY_RELEASE 0   // 1: spectra and key slot released right after the first FMA pass (all loads have returned by then): 19.26 ms
 #endif                        //    against 18.94 (the barrier traffic in the middle of the FMA block costs more than the earlier refill gains)
 #ifndef WS2_NAMED_BAR
-#define WS2_NAMED_BAR 0
-#endif
+#define WS2_NAMED_BAR 0       // 1: "spectra of a row pair ready" through hardware barriers 1-6 (FFT warps bar.arrive, MAC warps bar.sync) instead of
+#endif                        //    polled mbarriers: no polling instructions, but 19.71 ms against 18.93 (bar.sync re-aligns the eight MAC warps)
 #ifndef WS2_RFULL_PER_ROW
-#define WS2_RFULL_PER_ROW 0
+#define WS2_RFULL_PER_ROW 0   // 1: one spectra barrier per row instead of per row pair: 18.90 against 18.97 ms in the same run (noise)
 #endif
 #ifndef WS2_MAC_WIDE
 #define WS2_MAC_WIDE 1     // all K+1 key values of a row first, then four FMA passes over all (g, c): dependent FMAs 15 apart (19.17 -> 18.92 ms per 888)
