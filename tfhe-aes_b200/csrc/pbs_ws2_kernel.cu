@@ -45,6 +45,9 @@
 #ifndef WS2_RFULL_PER_ROW
 #define WS2_RFULL_PER_ROW 0   // 1: one spectra barrier per row instead of per row pair: 18.90 against 18.97 ms in the same run (noise)
 #endif
+#ifndef WS2_REVMAP
+#define WS2_REVMAP 1          // FFT groups in reverse warp order: row 0, which the MAC role needs first, sits on the warp the issue arbiter favours
+#endif                        //    (0: natural order, 20.07 ms against 18.96)
 #ifndef WS2_MAC_WIDE
 #define WS2_MAC_WIDE 1     // all K+1 key values of a row first, then four FMA passes over all (g, c): dependent FMAs 15 apart (19.17 -> 18.92 ms per 888)
 #endif
@@ -146,10 +149,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) pbs_ws2_kernel(PbsArgs a) {
         // ================================ FFT warps ================================================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(256 - MAC_REGS));
         const int ftid = tid - (WS_THREADS - WS_FFT_THREADS);
-        const int gid = 15 - (ftid >> 4), lane = ftid & 15;        // groups in reverse warp order (the arbiter favours high warp ids)
+        const int gid = WS2_REVMAP ? 15 - (ftid >> 4) : (ftid >> 4), lane = ftid & 15;   // groups in reverse warp order (the arbiter favours high warp ids)
         const bool active = gid < G * (K + 1);
         const int ct = active ? gid % G : 0, r = active ? gid / G : 0;
-        const int gid_a = 14 - (ftid >> 5) * 2, gid_b = gid_a + 1;
+        const int gid_a = WS2_REVMAP ? 14 - (ftid >> 5) * 2 : (ftid >> 5) * 2, gid_b = gid_a + 1;
         const int r_a = gid_a / G;
         const int r_b = (gid_b < G * (K + 1)) ? gid_b / G : r_a;
         (void)r_a;
