@@ -411,11 +411,11 @@ def test_opt_bootstrap_wave_both_schedules(engine_opt, oracle_opt, count):
     assert torus_absdiff(o.phase_big(res[2][sample]), o.phase_big(ref)) < 2 ** 36
 
 
-@pytest.mark.parametrize("count,schedule", [(7, 4), (900, 0), (1700, 0)])
+@pytest.mark.parametrize("count,schedule", [(7, 4), (900, 0), (1400, 0)])
 def test_opt_bootstrap_two_sets_per_cta(engine_opt, oracle_opt, count, schedule):
     """pbs_ws2_kernel (two sets of three ciphertexts per CTA, accumulators in tensor memory): same arithmetic as the
     warp-specialised kernel, so the outputs are bit-identical.  7 forced: ragged last CTA; 900 automatic: one wave of 888 + 12 through
-    the cluster kernel; 1700 automatic: 888 + a remainder above five sixths of a wave, all through pbs_ws2_kernel."""
+    the cluster kernel; 1400 automatic: 888 + a remainder above half a wave, all through pbs_ws2_kernel."""
     o = oracle_opt
     rng = np.random.default_rng(count)
     base = 60

@@ -312,14 +312,14 @@ int dev_pbs(tfa_ctx *ctx, const u64 *in, int count, const u64 *lut, u64 in_scale
     // remaining shapes (K = 1 test parameter sets with G > 1) and stays selectable for comparison.
     static const bool timing = getenv("TFA_PBS_TIMING") != nullptr;
     // Large batches: two sets of three ciphertexts per CTA taking turns (pbs_ws2_kernel.cu): 18.9 ms per wave of 888 against
-    // 2 x 10.1 ms.  Whole waves go to it; a remainder of more than five sixths of a wave too (two G = 3 waves would take 20.2 ms); a
-    // smaller remainder is served by the kernels below, which finish a partial wave sooner (10.1 + 7.6 ... 8.7 ms up to 740).
+    // 2 x 10.1 ms.  Whole waves go to it, and so does a remainder of more than half a wave (the kernels below would need two rounds of
+    // 148 CTAs for it: 20.2 ms); a smaller remainder is served by the kernels below, which finish a partial wave in 5-10 ms.
     static const bool no_ws2 = getenv("TFA_PBS_NO_WS2") != nullptr;
     if (ctx->k == 4 && ctx->p.pbs_base_log == 8 && ctx->p.pbs_level == 5 && !timing &&
         ((ctx->pbs_schedule == 0 && !no_ws2) || ctx->pbs_schedule == 4)) {
         const int wave = 6 * ctx->sm_count;
         int n2 = ctx->pbs_schedule == 4 ? count : (count / wave) * wave;
-        if (count - n2 > (5 * wave) / 6) n2 = count;
+        if (count - n2 > wave / 2) n2 = count;
         if (n2 > 0) {
             PbsArgs b = a;
             b.count = n2;
