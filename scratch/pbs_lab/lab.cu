@@ -64,6 +64,7 @@ int main(int argc, char **argv) {
     std::vector<uint64_t> href(out_words), hout(out_words);
     const int nv = sizeof(variants) / sizeof(variants[0]);
     const char *only = getenv("LAB_ONLY");
+    if (getenv("LAB_G")) for (int v = 0; v < nv; v++) variants[v].G = atoi(getenv("LAB_G"));   // ciphertexts per CTA (pbs_ws_kernel variants: 1, 2, 3)
     for (int v = 0; v < nv; v++) {
         if (only && v > 0 && !strstr(only, variants[v].name)) continue;
         a.out = v == 0 ? ref : out;
